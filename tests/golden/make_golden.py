@@ -1,0 +1,273 @@
+"""Generate the committed golden fixtures by running the UNMODIFIED reference (``/root/reference``) on CPU.
+
+Run in the build container only (the GPU box has no ``/root/reference``):
+
+    python tests/golden/make_golden.py
+
+The reference is imported read-only with the accommodations of SURVEY.md §8(c): stub modules for the
+optional viz/training deps, seeded synthetic assets written by ``robustcap_b200.synthetic.write_assets``
+and ``chdir`` into that asset tree so the reference's relative paths resolve.  Weights are NOT stored (254 MB):
+they are regenerated from ``(seed, variant)`` by ``robustcap_b200.synthetic.make_state_dict`` and loaded into
+the reference ``Net`` with ``load_state_dict``; inputs and reference outputs are stored as float32 ``.npz``.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+from robustcap_b200 import synthetic  # noqa: E402
+
+REF = '/root/reference'
+ASSET_SEED = 0
+
+
+def import_reference():
+    for name in ('trimesh', 'pyrender', 'smplx', 'wandb'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['smplx'].SMPL = object
+    thop = types.ModuleType('thop')
+    thop.clever_format = lambda *a, **k: ''
+    sys.modules['thop'] = thop
+    root = synthetic.default_asset_root()
+    synthetic.write_assets(root, ASSET_SEED)
+    os.chdir(root)
+    sys.path.insert(0, REF)
+    import warnings
+    warnings.filterwarnings('ignore')
+    import articulate as art
+    from net.sig_mp import Net
+    import net.sig_mp as sig
+    from net.smplify.run import smplify_runner
+    from net.smplify import temporal_smplify as ts
+    import config as rconfig
+    import utils as rutils
+    return dict(art=art, Net=Net, sig=sig, smplify_runner=smplify_runner, ts=ts, config=rconfig, utils=rutils)
+
+
+def gen_math(ref, out):
+    art = ref['art']
+    M = art.math
+    g = torch.Generator().manual_seed(11)
+    d = {}
+    r6d = torch.randn(64, 6, generator=g)
+    r6d[0] = 0  # NaN -> 0 path (angular.py:263)
+    r6d[1, 3:] = r6d[1, :3] * 2  # degenerate (parallel) pair
+    d['r6d'] = r6d
+    d['r6d_to_R'] = M.r6d_to_rotation_matrix(r6d)
+    R = synthetic._random_rotations(64, g)
+    d['R'] = R
+    d['R_to_r6d'] = M.rotation_matrix_to_r6d(R)
+    aa = torch.randn(64, 3, generator=g)
+    aa[0] = 0
+    aa[1] = torch.tensor([0.6 * np.pi, 0.8 * np.pi, 0.0])  # |theta| = pi
+    aa[2] *= 1e-5
+    d['aa'] = aa
+    d['aa_to_R'] = M.axis_angle_to_rotation_matrix(aa)
+    d['batch_rodrigues'] = ref['ts'].batch_rodrigues(aa)
+    # cv2.Rodrigues semantics incl. non-orthonormal inputs (angular.py:236-246)
+    Rn = torch.cat((R, d['aa_to_R'], R + 1e-3 * torch.randn(64, 3, 3, generator=g),
+                    torch.eye(3).expand(2, 3, 3)))
+    d['R_noisy'] = Rn
+    d['R_to_aa'] = M.rotation_matrix_to_axis_angle(Rn)
+    q = torch.randn(64, 4, generator=g)
+    d['q'] = q
+    d['q_to_R'] = M.quaternion_to_rotation_matrix(q)
+    d['q_to_aa'] = M.quaternion_to_axis_angle(q)
+    d['aa_to_q'] = M.axis_angle_to_quaternion(aa)
+    q2 = torch.randn(64, 4, generator=g)
+    d['q2'] = q2
+    d['q_prod'] = M.quaternion_product(q, q2)
+    d['q_inv'] = M.quaternion_inverse(q)
+    d['q_mean'] = M.quaternion_mean(q)
+    d['angle_between'] = M.angle_between(R[:32], R[32:])
+    np.savez_compressed(os.path.join(out, 'math.npz'), **{k: v.numpy() for k, v in d.items()})
+
+
+def gen_kinematics(ref, out):
+    art = ref['art']
+    bm = art.ParametricModel('models/SMPL_male.pkl')
+    g = torch.Generator().manual_seed(12)
+    d = {}
+    B = 5
+    pose = synthetic._random_rotations(B * 24, g).view(B, 24, 3, 3)
+    tran = torch.randn(B, 3, generator=g)
+    shape = torch.randn(B, 10, generator=g)
+    d['pose'], d['tran'], d['shape'] = pose, tran, shape
+    j0, v0 = bm.get_zero_pose_joint_and_vertex()
+    d['zero_j'], d['zero_v'] = j0, v0
+    js, vs = bm.get_zero_pose_joint_and_vertex(shape[:2])
+    d['zero_j_shape'], d['zero_v_shape'] = js, vs
+    d['bone'] = bm.joint_position_to_bone_vector(j0.unsqueeze(0))
+    d['bone_to_joint'] = bm.bone_vector_to_joint_position(d['bone'])
+    d['fk_R'] = bm.forward_kinematics_R(pose)
+    d['ik_R'] = bm.inverse_kinematics_R(d['fk_R'])
+    T_local = art.math.transformation_matrix(pose, d['bone'].expand(B, 24, 3))
+    d['T_local'] = T_local
+    d['fk_T'] = bm.forward_kinematics_T(T_local)
+    d['ik_T'] = bm.inverse_kinematics_T(d['fk_T'])
+    d['inv_T'] = art.math.inverse_transformation_matrix(T_local)
+    gr, gj = bm.forward_kinematics(pose, tran=tran)
+    d['fk_grot'], d['fk_joint'] = gr, gj
+    gr, gj, gv = bm.forward_kinematics(pose, tran=tran, calc_mesh=True)
+    d['fk_mesh_joint'], d['fk_mesh_vert'] = gj, gv[:2]
+    d['fk_mesh_vert_mp'] = ref['utils'].sync_mp3d_from_smpl(gv, gj)
+    gr, gj, gv = bm.forward_kinematics(pose[:2], shape=shape[:2], tran=tran[:2], calc_mesh=True)
+    d['fk_shape_joint'], d['fk_shape_vert'] = gj, gv
+    kp = torch.randn(7, 33, 3, generator=g)
+    d['kp'] = kp
+    d['bbox_scale'] = ref['sig'].get_bbox_scale(kp)
+    d['mp_mask'] = torch.tensor(ref['config'].mp_mask)
+    d['ji_mask'] = torch.tensor(ref['config'].ji_mask)
+    d['vi_mask'] = torch.tensor(ref['config'].vi_mask)
+    d['parent'] = torch.tensor([-1] + bm.parent[1:])
+    np.savez_compressed(os.path.join(out, 'kinematics.npz'), **{k: v.numpy() for k, v in d.items()})
+
+
+# (name, weight seed, variant, conf mode, input seed, start, T)
+ONLINE_CASES = [
+    ('mixed_ff', 0, 'default', 'mixed', 1, 'first_frame', 48),
+    ('mixed_ft', 0, 'default', 'mixed', 2, 'first_tran', 48),
+    ('high_none', 0, 'default', 'high', 3, 'none', 32),
+    ('mid_ft', 0, 'default', 'mid', 4, 'first_tran', 32),
+    ('low_ff', 0, 'default', 'low', 5, 'first_frame', 32),
+    ('occl_ft', 0, 'default', 'occluded', 6, 'first_tran', 48),
+    ('contact_mixed_ft', 0, 'contact', 'mixed', 7, 'first_tran', 64),
+    ('contact_high_none', 0, 'contact', 'high', 8, 'none', 64),
+    ('snap_high_ft', 0, 'snap', 'high', 9, 'first_tran', 32),
+    ('contact_low_ff', 0, 'contact', 'low', 10, 'first_frame', 32),
+]
+
+
+def run_online(ref, sd, inp, start, record=None):
+    Net = ref['Net']
+    net = Net()
+    net.load_state_dict(sd)
+    net.eval()
+    Net.gravityc = inp['gravity'].clone()
+    T = inp['j2dc'].shape[1]
+    hooks = []
+    if record is not None:
+        for k in (2, 3, 4, 6, 7, 8):
+            def mk(k):
+                def hook(mod, args, output):
+                    record.append((k, output.detach().clone().flatten()))
+                return hook
+            hooks.append(getattr(net, 'rnn%d' % k).linear2.register_forward_hook(mk(k)))
+    poses, trans = [], []
+    for t in range(T):
+        kw = {}
+        if t == 0 and start == 'first_frame':
+            kw['first_frame'] = True
+        if t == 0 and start == 'first_tran':
+            kw['first_tran'] = torch.tensor([0.0, 0.0, 4.0])
+        p, tr = net.forward_online(inp['j2dc'][0, t], inp['accc'][0, t], inp['oric'][0, t], **kw)
+        poses.append(p)
+        trans.append(tr)
+    for h in hooks:
+        h.remove()
+    floor_n = len(net.floor_y)
+    net.reset_states()
+    return torch.stack(poses), torch.stack(trans), floor_n
+
+
+def gen_online(ref, out):
+    cache = {}
+    for name, wseed, variant, conf, iseed, start, T in ONLINE_CASES:
+        key = (wseed, variant)
+        if key not in cache:
+            cache[key] = synthetic.make_state_dict(wseed, variant)
+        inp = synthetic.make_inputs(1, T, seed=iseed, conf=conf)
+        rec = []
+        pose, tran, floor_n = run_online(ref, cache[key], inp, start, rec)
+        d = {'j2dc': inp['j2dc'][0], 'accc': inp['accc'][0], 'oric': inp['oric'][0], 'gravity': inp['gravity'],
+             'pose': pose, 'tran': tran, 'floor_n': torch.tensor(floor_n)}
+        # sub-net outputs in call order for the first 6 frames (debug aid: which net diverged first)
+        ncall = min(len(rec), 6 * 8)
+        d['rec_net'] = torch.tensor([k for k, _ in rec[:ncall]])
+        width = 144
+        d['rec_out'] = torch.stack([torch.nn.functional.pad(o, (0, width - o.numel())) for _, o in rec[:ncall]])
+        np.savez_compressed(os.path.join(out, 'online_%s.npz' % name), **{k: v.numpy() for k, v in d.items()})
+        print('online', name, 'floor samples', floor_n, 'max |tran|', float(tran.abs().max()))
+
+
+SMPLIFY_CASES = [('it5', 5, 24), ('it20', 20, 16)]
+
+
+def gen_smplify(ref, out):
+    ts = ref['ts']
+    art = ref['art']
+    sd = synthetic.make_state_dict(0, 'default')
+    for name, max_iter, T in SMPLIFY_CASES:
+        inp = synthetic.make_inputs(1, T, seed=21, conf='high')
+        pose, tran, _ = run_online(ref, sd, inp, 'first_tran')
+        cam_k = torch.tensor([[1000.0, 0, 960], [0, 1000, 540], [0, 0, 1]])
+        bm = art.ParametricModel('models/SMPL_male.pkl')
+        _, joint, vert = bm.forward_kinematics(pose, tran=tran, calc_mesh=True)
+        j = ref['utils'].sync_mp3d_from_smpl(vert, joint)
+        g = torch.Generator().manual_seed(22)
+        uv = (cam_k @ (j / j[..., 2:]).unsqueeze(-1)).squeeze(-1)[..., :2] + 5 * torch.randn(T, 33, 2, generator=g)
+        j2d_pix = torch.cat((uv, 0.5 + 0.5 * torch.rand(T, 33, 1, generator=g)), dim=-1)
+        imu_ori = inp['oric'][0]
+        d = {'pose_in': pose, 'tran_in': tran, 'j2d_pix': j2d_pix.clone(), 'imu_ori': imu_ori, 'cam_k': cam_k}
+        # loss value and gradient at the initial point (analytic-gradient check)
+        sm = ts.TemporalSMPLify(cam_k=cam_k, imu_ori=imu_ori, step_size=1e-3, num_iters=1, use_lbfgs=True,
+                                batch_size=T, max_iter=max_iter)
+        kp = j2d_pix.clone()
+        joints_conf = kp[:, :, -1]
+        joints_conf[:, sm.ign_mp_joints] = 0.
+        body_pose = art.math.rotation_matrix_to_axis_angle(pose).reshape(T, -1).clone().requires_grad_(True)
+        gt = tran.clone().requires_grad_(True)
+        _, j0, v0 = bm.forward_kinematics(pose, tran=tran, calc_mesh=True)
+        ref3d = ref['utils'].sync_mp3d_from_smpl(v0, j0).detach()
+        R = ts.batch_rodrigues(body_pose.view(-1, 3)).view(T, -1, 3, 3)
+        gp, jj, vv = bm.forward_kinematics(R, tran=gt, calc_mesh=True)
+        mj = ref['utils'].sync_mp3d_from_smpl(vv, jj)
+        from net.smplify.losses import temporal_body_fitting_loss
+        loss = temporal_body_fitting_loss(body_pose, mj, kp[:, :, :2], joints_conf, sm.pose_prior, cam_k, ref3d,
+                                          imu_ori, gp[:, [ts.joint_mask]])
+        loss.backward()
+        d['aa_init'] = body_pose.detach()
+        d['loss_init'] = loss.detach()
+        d['grad_pose'] = body_pose.grad
+        d['grad_tran'] = gt.grad
+        d['reproj_init'] = sm.get_fitting_loss(pose, tran, j2d_pix.clone())
+        # the optimisation itself, exactly as smplify_runner does but with max_iter exposed
+        po, to, rl = sm(pose.reshape(T, -1).detach(), tran.detach(), j2d_pix.clone())
+        d['pose_out'], d['tran_out'], d['reproj_out'] = po.reshape(T, 24, 3, 3), to, rl
+        if max_iter == 20:
+            p2, t2, upd = ref['smplify_runner'](pose, tran, j2d_pix.clone(), imu_ori, batch_size=T, lr=1e-3,
+                                                use_lbfgs=True, opt_steps=1, cam_k=cam_k, loss_threshold=1e12)
+            d['runner_pose'], d['runner_tran'], d['runner_update'] = p2, t2, upd
+            p3, t3, upd3 = ref['smplify_runner'](pose, tran, j2d_pix.clone(), imu_ori, batch_size=T, lr=1e-3,
+                                                 use_lbfgs=True, opt_steps=1, cam_k=cam_k, loss_threshold=1e-3)
+            assert upd3 is None
+        np.savez_compressed(os.path.join(out, 'smplify_%s.npz' % name),
+                            **{k: (v.numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()})
+        print('smplify', name, 'loss_init', float(loss), 'moved', float((po.reshape(T, 24, 3, 3) - pose).abs().max()))
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ref = import_reference()
+    which = sys.argv[1:] or ['math', 'kinematics', 'online', 'smplify']
+    with torch.no_grad():
+        if 'math' in which:
+            gen_math(ref, HERE)
+        if 'kinematics' in which:
+            gen_kinematics(ref, HERE)
+        if 'online' in which:
+            gen_online(ref, HERE)
+    if 'smplify' in which:
+        gen_smplify(ref, HERE)
+    print('done')
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,144 @@
+"""Pin the oracle against outputs of the reference itself (tests/golden/*.npz, made by make_golden.py).
+
+CPU only.  Tolerances: the oracle restates the same float32 math with (mostly) the same ATen ops, so rotation
+conversions / FK agree to a few ulp; the 6-LSTM loop agrees to float32 re-association noise (the reference uses
+oneDNN's fused LSTM, the oracle writes the cell out), bounded here at 6e-5 rad / 2e-5 m over the stored frames —
+well inside the product bars of 1e-4 rad / 1 mm.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rotations as R
+from oracle import kinematics as K
+from oracle.fusion import FusionOracle
+from robustcap_b200 import synthetic
+
+
+def T(x):
+    return torch.from_numpy(np.asarray(x))
+
+
+def load(golden_dir, name):
+    return {k: T(v) for k, v in np.load(os.path.join(golden_dir, name)).items()}
+
+
+def close(a, b, tol):
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    assert err <= tol, err
+
+
+def test_math(golden_dir):
+    g = load(golden_dir, 'math.npz')
+    close(R.r6d_to_matrix(g['r6d']), g['r6d_to_R'], 1e-6)
+    assert torch.equal(R.matrix_to_r6d(g['R']), g['R_to_r6d'])
+    close(R.axis_angle_to_matrix(g['aa']), g['aa_to_R'], 1e-6)
+    close(R.batch_rodrigues(g['aa']), g['batch_rodrigues'], 1e-6)
+    assert torch.equal(R.matrix_to_axis_angle_cv2(g['R_noisy']), g['R_to_aa'])
+    close(R.matrix_to_axis_angle(g['R_noisy']), g['R_to_aa'], 2e-6)
+    close(R.quaternion_to_matrix(g['q']), g['q_to_R'], 1e-6)
+    close(R.quaternion_to_axis_angle(g['q']), g['q_to_aa'], 1e-5)
+    close(R.axis_angle_to_quaternion(g['aa']), g['aa_to_q'], 1e-6)
+    close(R.quaternion_product(g['q'], g['q2']), g['q_prod'], 1e-6)
+    assert torch.equal(R.quaternion_inverse(g['q']), g['q_inv'])
+    close(R.quaternion_mean(g['q']), g['q_mean'], 1e-6)
+    close(R.angle_between(g['R'][:32], g['R'][32:]), g['angle_between'], 1e-5)
+
+
+def test_kinematics(golden_dir, assets):
+    g = load(golden_dir, 'kinematics.npz')
+    body = K.BodyOracle(assets['smpl_file'])
+    assert [-1] + body.parent[1:] == g['parent'].tolist()
+    j0, v0 = body.zero_pose()
+    assert torch.equal(j0, g['zero_j']) and torch.equal(v0, g['zero_v'])
+    js, vs = body.zero_pose(g['shape'][:2])
+    close(js, g['zero_j_shape'], 1e-6)
+    close(vs, g['zero_v_shape'], 1e-6)
+    bone = K.joint_to_bone(j0.unsqueeze(0), body.parent)
+    assert torch.equal(bone, g['bone'])
+    assert torch.equal(K.bone_to_joint(bone, body.parent), g['bone_to_joint'])
+    close(K.fk_R(g['pose'], body.parent), g['fk_R'], 1e-6)
+    close(K.ik_R(g['fk_R'], body.parent), g['ik_R'], 1e-6)
+    close(K.fk_T(g['T_local'], body.parent), g['fk_T'], 1e-6)
+    close(K.ik_T(g['fk_T'], body.parent), g['ik_T'], 1e-5)
+    close(K.invert_T(g['T_local']), g['inv_T'], 1e-6)
+    gr, gj = body.forward_kinematics(g['pose'], tran=g['tran'])
+    close(gr, g['fk_grot'], 1e-6)
+    close(gj, g['fk_joint'], 1e-6)
+    gr, gj, gv = body.forward_kinematics(g['pose'], tran=g['tran'], calc_mesh=True)
+    close(gj, g['fk_mesh_joint'], 1e-6)
+    close(gv[:2], g['fk_mesh_vert'], 2e-6)
+    from oracle.fusion import MP_MASK
+    assert MP_MASK == g['mp_mask'].tolist()
+    close(K.mediapipe_points(gv, gj, MP_MASK), g['fk_mesh_vert_mp'], 2e-6)
+    gr, gj, gv = body.forward_kinematics(g['pose'][:2], shape=g['shape'][:2], tran=g['tran'][:2], calc_mesh=True)
+    close(gj, g['fk_shape_joint'], 2e-6)
+    close(gv, g['fk_shape_vert'], 2e-6)
+    close(K.bbox_scale(g['kp']), g['bbox_scale'], 0)
+
+
+def _case_meta():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        'make_golden', os.path.join(os.path.dirname(__file__), 'golden', 'make_golden.py'))
+    src = open(spec.origin).read()
+    # parse ONLINE_CASES without importing the reference
+    start = src.index('ONLINE_CASES = [')
+    end = src.index(']\n', start) + 1
+    ns = {}
+    exec(src[start:end], ns)
+    return ns['ONLINE_CASES']
+
+
+ONLINE_CASES = _case_meta()
+_SD = {}
+
+
+def get_sd(seed, variant):
+    if (seed, variant) not in _SD:
+        _SD[(seed, variant)] = synthetic.make_state_dict(seed, variant)
+    return _SD[(seed, variant)]
+
+
+def pose_angle(a, b):
+    """Geodesic angle (rad) between rotation matrices, float64 trace formula with a small-angle safe branch."""
+    a, b = a.double().reshape(-1, 3, 3), b.double().reshape(-1, 3, 3)
+    d = a.transpose(1, 2) @ b
+    s = 0.5 * torch.stack((d[:, 2, 1] - d[:, 1, 2], d[:, 0, 2] - d[:, 2, 0], d[:, 1, 0] - d[:, 0, 1]), 1).norm(dim=1)
+    c = 0.5 * (d[:, 0, 0] + d[:, 1, 1] + d[:, 2, 2] - 1)
+    return torch.atan2(s, c)
+
+
+@pytest.mark.parametrize('case', ONLINE_CASES, ids=[c[0] for c in ONLINE_CASES])
+@pytest.mark.parametrize('impl', ['manual', 'aten'])
+def test_online(golden_dir, assets, case, impl):
+    name, wseed, variant, conf, iseed, start, Tn = case
+    g = load(golden_dir, 'online_%s.npz' % name)
+    # inputs are reproducible from the seed alone
+    inp = synthetic.make_inputs(1, Tn, seed=iseed, conf=conf)
+    assert torch.equal(inp['j2dc'][0], g['j2dc']) and torch.equal(inp['oric'][0], g['oric'])
+    body = K.BodyOracle(assets['smpl_file'])
+    net = FusionOracle(get_sd(wseed, variant), body, lstm_impl=impl)
+    kw = {'first_frame': True} if start == 'first_frame' else (
+        {'first_tran': torch.tensor([0., 0., 4.])} if start == 'first_tran' else {})
+    trace = []
+    pose, tran = net.run(g['j2dc'], g['accc'], g['oric'], gravity=g['gravity'], trace=trace, **kw)
+    assert len(net.floor_y) == int(g['floor_n'])
+    # same sub-net call order as the reference (hooks on linear2) and matching outputs
+    n = g['rec_net'].numel()
+    assert [k for k, _ in trace[:n]] == g['rec_net'].tolist()
+    for i in range(n):
+        close(trace[i][1], g['rec_out'][i, :trace[i][1].numel()], 2e-5)
+    ang = pose_angle(pose, g['pose']).max().item()
+    terr = (tran - g['tran']).abs().max().item()
+    # measured: the reference itself sits up to 3.6e-5 rad from a float64 evaluation of the same weights
+    # (case contact_low_ff); the written-out float32 cell is within 1e-5 rad of float64.
+    assert ang < 6e-5, ang
+    assert terr < 2e-5, terr
+    if impl == 'aten':
+        # same ATen kernels as the reference -> bit-identical at equal thread count
+        assert ang < 1e-6 and terr < 1e-6
