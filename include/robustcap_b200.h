@@ -1,0 +1,156 @@
+/* robustcap_b200 — C ABI of the B200-native RobustCap hot path (fusion LSTM stack + SMPL kinematics + SMPLify).
+ *
+ * The reference (shaohua-pan/RobustCap) is pure Python and has no FFI layer; its "plugin boundary" for this path
+ * is the Python import surface consumed by evaluate.py:1-17 and live_server.py:5-9.  This header is the C-ABI
+ * that a reference maintainer binds (ctypes) to replace the arithmetic behind that surface.
+ * Every entry point cites the reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - Pointers named d_* are DEVICE pointers (float32 unless noted), h_* are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls only enqueue work unless
+ *     documented otherwise; the caller synchronises.
+ *   - Matrices are row-major; rotation matrices [..,3,3]; quaternions wxyz.
+ *   - Return value: 0 on success, negative rc_status on failure; rc_last_error() returns a message
+ *     (thread-local).  No entry point falls back to a CPU computation: without a usable CUDA device every
+ *     compute call returns RC_ERR_CUDA.
+ *   - Handles are thread-compatible (one thread at a time per handle); no ownership of caller buffers is taken.
+ */
+#ifndef ROBUSTCAP_B200_H
+#define ROBUSTCAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum rc_status {
+    RC_OK = 0,
+    RC_ERR_ARG = -1,      /* bad argument (null pointer, size mismatch, unknown tensor name) */
+    RC_ERR_CUDA = -2,     /* CUDA runtime error, incl. no device */
+    RC_ERR_STATE = -3,    /* call order violated (e.g. net not finalised) */
+    RC_ERR_ALLOC = -4
+} rc_status;
+
+typedef struct rc_model rc_model;   /* SMPL constants on the device          (articulate/model.py:17-40)   */
+typedef struct rc_net rc_net;       /* packed weights of the six LSTM stacks (net/sig_mp.py:47-93)         */
+typedef struct rc_state rc_state;   /* per-stream recurrent + tracker state for B streams (sig_mp.py:85-104) */
+
+const char* rc_version(void);
+const char* rc_last_error(void);
+/* Number of this library's kernels launched by the calling process so far (bench.py "gpu_launches"). */
+int64_t rc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Rotation representations — articulate/math/angular.py (N independent items, contiguous).
+ * ------------------------------------------------------------------------------------------------------- */
+int rc_r6d_to_rotmat(const float* d_r6d, float* d_R, int64_t n, void* stream);        /* angular.py:249-264 */
+int rc_rotmat_to_r6d(const float* d_R, float* d_r6d, int64_t n, void* stream);        /* angular.py:267-274 */
+int rc_axis_angle_to_rotmat(const float* d_aa, float* d_R, int64_t n, void* stream);  /* angular.py:221-233 */
+int rc_rotmat_to_axis_angle(const float* d_R, float* d_aa, int64_t n, void* stream);  /* angular.py:236-246 (cv2.Rodrigues semantics) */
+int rc_batch_rodrigues(const float* d_aa, float* d_R, int64_t n, void* stream);       /* net/smplify/temporal_smplify.py:25-59 */
+int rc_quat_to_rotmat(const float* d_q, float* d_R, int64_t n, void* stream);         /* angular.py:306-318 */
+int rc_quat_to_axis_angle(const float* d_q, float* d_aa, int64_t n, void* stream);    /* angular.py:277-290 */
+int rc_axis_angle_to_quat(const float* d_aa, float* d_q, int64_t n, void* stream);    /* angular.py:293-303 */
+int rc_quat_product(const float* d_q1, const float* d_q2, float* d_q, int64_t n, void* stream); /* angular.py:79-93 */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Kinematic tree — articulate/math/spatial.py.  `h_parent` is a HOST int32[nj] table, parent[0] < 0,
+ * parent[i] < i; nj <= 64.  b = number of frames.
+ * ------------------------------------------------------------------------------------------------------- */
+int rc_tree_fk_R(const float* d_Rl, float* d_Rg, const int32_t* h_parent, int nj, int64_t b, void* stream);   /* spatial.py:170-194 */
+int rc_tree_ik_R(const float* d_Rg, float* d_Rl, const int32_t* h_parent, int nj, int64_t b, void* stream);   /* spatial.py:197-221 */
+int rc_tree_fk_T(const float* d_Tl, float* d_Tg, const int32_t* h_parent, int nj, int64_t b, void* stream);   /* spatial.py:224-249, [b,nj,4,4] */
+int rc_tree_ik_T(const float* d_Tg, float* d_Tl, const int32_t* h_parent, int nj, int64_t b, void* stream);   /* spatial.py:252-277 */
+int rc_tree_bone_to_joint(const float* d_bone, float* d_joint, const int32_t* h_parent, int nj, int64_t b, void* stream); /* spatial.py:126-145 */
+int rc_tree_joint_to_bone(const float* d_joint, float* d_bone, const int32_t* h_parent, int nj, int64_t b, void* stream); /* spatial.py:148-167 */
+
+/* ---------------------------------------------------------------------------------------------------------
+ * SMPL body model — articulate/model.py:17-241.
+ * rc_model_create copies the (host) constants: zero-pose joints J[24,3] and vertices v[nv,3] (both already
+ * root-centred as get_zero_pose_joint_and_vertex returns them, model.py:87), skinning weights [nv,24], parent
+ * table, and the 33-entry MediaPipe vertex table (config.py:99).
+ * ------------------------------------------------------------------------------------------------------- */
+int rc_model_create(rc_model** out, const float* h_joints, const float* h_verts, const float* h_skin_w,
+                    int32_t nv, const int32_t* h_parent, const int32_t* h_mp_mask);
+void rc_model_destroy(rc_model* m);
+/* ParametricModel.forward_kinematics (model.py:209-241).
+ *   d_pose [b,24,3,3] local rotations; d_tran [b,3] or NULL; d_joints_rest/d_verts_rest: per-frame zero-pose
+ *   joints [b,24,3] / vertices [b,nv,3] for shaped bodies, or NULL for the model's mean shape.
+ *   Outputs: d_Rg [b,24,3,3], d_joint [b,24,3]; d_vert [b,nv,3] when not NULL (calc_mesh=True). */
+int rc_model_forward_kinematics(const rc_model* m, const float* d_pose, const float* d_tran,
+                                const float* d_joints_rest, const float* d_verts_rest, int64_t b,
+                                float* d_Rg, float* d_joint, float* d_vert, void* stream);
+/* The 33 synthetic MediaPipe points only (net/sig_mp.py:287-299 on top of model.py:209-241): d_kp [b,33,3].
+ * Skins just the 21 vertices sync_mp3d reads instead of all 6890. */
+int rc_model_keypoints(const rc_model* m, const float* d_pose, const float* d_tran, int64_t b,
+                       float* d_joint, float* d_kp, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fusion network — net/sig_mp.py:23-274 (class Net) on top of articulate/utils/torch/rnn.py:92-219.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct rc_net_config {      /* Net class attributes, sig_mp.py:27-45 and :91-93 */
+    double conf_lo, conf_hi;        /* conf_range            (0.7, 0.8); live (0.85, 0.9) */
+    double tran_filter_num;         /* tran_filter_num       0.05; live 0.01              */
+    float contact_threshold;        /* 0.7  */
+    float height_threshold;         /* height_threhold 0.15 */
+    float distance_threshold;       /* distrance_threshold 10 */
+    int32_t use_flat_floor;         /* 1 */
+    int32_t live;                   /* 0 */
+    int32_t update_vision_freq;     /* 30 */
+} rc_net_config;
+
+void rc_net_default_config(rc_net_config* cfg, int live);
+int rc_net_create(rc_net** out, const rc_model* model, const rc_net_config* cfg);
+void rc_net_destroy(rc_net* n);
+int rc_net_set_config(rc_net* n, const rc_net_config* cfg);
+/* Net.load_state_dict: one call per state_dict entry (key set of SURVEY.md §5, e.g. "rnn4.rnn.weight_hh_l1",
+ * "rnn2.init_net.2.bias"); h_data is HOST float32, numel must match.  Then rc_net_finalize packs the tensors
+ * into the device layout (gate-interleaved [4H, 2H] LSTM blocks, K padded to 16) and frees the staging copy. */
+int rc_net_set_tensor(rc_net* n, const char* key, const float* h_data, int64_t numel);
+int rc_net_finalize(rc_net* n);
+int64_t rc_net_weight_bytes(const rc_net* n);     /* bytes of packed per-frame weights resident in HBM */
+
+int rc_state_create(rc_state** out, const rc_net* net, int32_t b);
+void rc_state_destroy(rc_state* s);
+int rc_state_reset(rc_state* s, void* stream);                                   /* Net.reset_states, sig_mp.py:95-104 */
+int rc_state_set_gravity(rc_state* s, const float* h_gravity3, void* stream);   /* Net.gravityc, one value for all streams */
+
+/* flag bits for d_row_flags */
+#define RC_ROW_FIRST_FRAME 1   /* forward_online(first_frame=True) */
+#define RC_ROW_FIRST_TRAN 2    /* forward_online(first_tran=...)   */
+
+/* Net.forward_online for B streams, one frame (sig_mp.py:113-274).
+ *   d_j2dc [b,33,3], d_accc [b,6,3], d_oric [b,6,3,3]; d_first_tran [b,3] or NULL; d_row_flags int32[b] or NULL;
+ *   d_gravity [b,3] per-stream gravity or NULL (use rc_state_set_gravity value);
+ *   any_first_frame: host hint, non-zero when some row has RC_ROW_FIRST_FRAME (adds the extra rnn6 pass of
+ *   sig_mp.py:155-156).  Outputs d_pose [b,24,3,3], d_tran [b,3]. */
+int rc_forward_step(rc_state* s, const float* d_j2dc, const float* d_accc, const float* d_oric,
+                    const float* d_gravity, const float* d_first_tran, const int32_t* d_row_flags,
+                    int any_first_frame, float* d_pose, float* d_tran, void* stream);
+
+/* forward_offline := reset_states + forward_online over t (evaluate.py:75-85,93), batched over B sequences.
+ *   d_j2dc [b,T,33,3], d_accc [b,T,6,3], d_oric [b,T,6,3,3]; d_lengths int32[b] or NULL (ragged batch: rows
+ *   stop advancing after their length; outputs beyond it are left untouched);
+ *   first-frame arguments apply to t = 0.  Outputs d_pose [b,T,24,3,3], d_tran [b,T,3].
+ *   use_graph != 0 replays one captured CUDA graph per frame for t >= 1. */
+int rc_forward_sequence(rc_state* s, int32_t T, const float* d_j2dc, const float* d_accc, const float* d_oric,
+                        const int32_t* d_lengths, const float* d_gravity, const float* d_first_tran,
+                        const int32_t* d_row_flags, int any_first_frame, float* d_pose, float* d_tran,
+                        int use_graph, void* stream);
+
+/* Same with HOST buffers (pinned recommended): copies inputs H2D, runs, copies results D2H and synchronises
+ * the stream — the end-to-end call of the plugin. */
+int rc_forward_sequence_host(rc_state* s, int32_t T, const float* h_j2dc, const float* h_accc, const float* h_oric,
+                             const int32_t* h_lengths, const float* h_first_tran, const int32_t* h_row_flags,
+                             float* h_pose, float* h_tran, int use_graph, void* stream);
+
+/* Debug / test taps: copy a sub-net output of the last step to the host: which in {2,3,4,6,7,8}; out has
+ * b * width floats (width = 69,3,69,3,144,2). */
+int rc_state_debug_output(rc_state* s, int which, float* h_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROBUSTCAP_B200_H */

@@ -1,0 +1,617 @@
+// Net.forward_online / forward_offline for B independent streams (net/sig_mp.py:23-274).
+//
+// Per frame the host enqueues (no host<->device sync anywhere, unlike the reference's .item() at :138):
+//   prep    — confidence, IMU change of frame, key-point normalisation, sub-net inputs, branch flags
+//   lists   — compacts the branch flags into row lists (all / vision / rnn6-first-frame / rnn6 / late)
+//   rnn2, rnn3 (all rows) ; rnn4, rnn6 (vision rows) ; mid (lerp) ; rnn7, rnn8 (all rows)
+//   kin     — 6D->R, IK, foot FK, translation state machine, SMPL FK of the 33 key points, vision-updater inputs
+//   init    — rnn2.init_net re-seed for rows that reached c >= hi for the first time (:178-183)
+//   rnn6, rnn4 late pass on the synthetic key points (:263-271), outputs discarded (linear2 skipped)
+// Each sub-net pass = linear1+relu -> fused LSTM layer 0 -> fused LSTM layer 1 -> commit(h) [-> linear2].
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+#include <string.h>
+#include "rc_common.cuh"
+#include "rc_rows.h"
+#include "rc_model.cuh"
+#include "rc_linear.cuh"
+#include "rc_pack.h"
+
+namespace {
+
+enum { NET2 = 0, NET3, NET4, NET6, NET7, NET8, NNETS };
+const int kNetId[NNETS] = {2, 3, 4, 6, 7, 8};
+const int kNetIn[NNETS] = {72, 141, 171, 240, 141, 141};
+const int kNetK1[NNETS] = {RC_K2, RC_K3, RC_K4, RC_K6, RC_K7, RC_K7};
+const int kNetH[NNETS] = {512, 512, 1280, 1024, 512, 512};
+const int kNetOut[NNETS] = {69, 3, 69, 3, 144, 2};
+const int kInitDims[4] = {69, 512, 1024, 2048};
+constexpr int kInitK0 = 80;
+
+enum { L_ALL = 0, L_HI, L_6A, L_6B, L_LATE, L_INIT, NLISTS };
+
+struct NetDev {
+    int in = 0, K1 = 0, H = 0, out = 0, out4 = 0;
+    float *W1 = nullptr, *b1 = nullptr, *WL[2] = {nullptr, nullptr}, *bL[2] = {nullptr, nullptr}, *W2 = nullptr, *b2 = nullptr;
+};
+struct NetBuf {
+    float *h[2] = {nullptr, nullptr}, *c[2] = {nullptr, nullptr}, *hn[2] = {nullptr, nullptr}, *a1 = nullptr;
+};
+
+}  // namespace
+
+struct rc_net {
+    const rc_model* model = nullptr;
+    RcNetCfg cfg;
+    std::map<std::string, std::vector<float>> staging;
+    bool finalized = false;
+    NetDev nets[NNETS];
+    float *Wi[3] = {nullptr, nullptr, nullptr}, *bi[3] = {nullptr, nullptr, nullptr};   // init_net
+    int64_t weight_bytes = 0;
+    std::vector<void*> allocs;
+};
+
+struct rc_state {
+    const rc_net* net = nullptr;
+    int B = 0;
+    std::vector<void*> allocs;
+    NetBuf nb[NNETS];
+    float *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *X6 = nullptr, *X7 = nullptr, *XI = nullptr;
+    float *Y3 = nullptr, *Y6 = nullptr, *Y7 = nullptr, *Y8 = nullptr, *Ydump = nullptr;
+    float *I1 = nullptr, *I2 = nullptr, *I3 = nullptr;
+    float *rcr = nullptr, *conf = nullptr, *lerpw = nullptr, *gravity = nullptr;
+    int* flags = nullptr;
+    int* lists = nullptr;      // [NLISTS][B]
+    int* counts = nullptr;     // [NLISTS]
+    int* d_t = nullptr;        // device frame cursor (sequence mode)
+    RcRowState* rows = nullptr;
+    // cached CUDA graph of one steady-state frame
+    cudaGraphExec_t graph = nullptr;
+    std::vector<const void*> graph_key;
+    // staging buffers of rc_forward_sequence_host
+    float *hj = nullptr, *ha = nullptr, *ho = nullptr, *hp = nullptr, *ht = nullptr, *hft = nullptr;
+    int *hlen = nullptr, *hfl = nullptr;
+    int64_t host_cap_T = 0;
+};
+
+namespace {
+
+struct StepIO {
+    const float *j2dc, *accc, *oric;       // bases
+    long long sj, sa, so;                  // per-stream strides (floats)
+    const float* gravity;                  // [B,3] or nullptr
+    const float* first_tran;               // [B,3] or nullptr
+    const int* row_flags;                  // [B] or nullptr
+    const int* lengths;                    // [B] or nullptr
+    float *pose, *tran;                    // bases
+    long long sp, st;                      // per-stream strides
+    const int* d_t;                        // frame cursor or nullptr (t = 0)
+    int first_mode;                        // 0 never, 1 always, 2 only at t == 0
+};
+
+__global__ void __launch_bounds__(128) rc_prep_kernel(RcNetCfg cfg, const RcRowState* __restrict__ rows, StepIO io, int B,
+                                                       float* X2, float* X3, float* X4, float* X6, float* X7,
+                                                       float* rcr, float* conf, float* lerpw, int* flags) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int t = io.d_t ? *io.d_t : 0;
+    int inflags = 0;
+    if (io.row_flags && (io.first_mode == 1 || (io.first_mode == 2 && t == 0))) inflags = io.row_flags[b] & 3;
+    if (!io.first_tran) inflags &= ~RC_F_FIRST_TRAN;
+    const bool active = !io.lengths || t < io.lengths[b];
+    if (!active) { flags[b] = 0; return; }
+    inflags |= RC_F_ACTIVE;
+    float kp[99], acc[18], ori[54];
+    const float* pj = io.j2dc + b * io.sj + (long long)t * 99;
+    const float* pa = io.accc + b * io.sa + (long long)t * 18;
+    const float* po = io.oric + b * io.so + (long long)t * 54;
+    for (int i = 0; i < 99; ++i) kp[i] = pj[i];
+    for (int i = 0; i < 18; ++i) acc[i] = pa[i];
+    for (int i = 0; i < 54; ++i) ori[i] = po[i];
+    flags[b] = rc_prep_row(cfg, rows[b], kp, acc, ori, inflags, X2 + (size_t)b * RC_K2, X3 + (size_t)b * RC_K3,
+                           X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6, X7 + (size_t)b * RC_K7, rcr + b * 9,
+                           conf + b, lerpw + b * 2);
+}
+
+// one warp per list: ordered compaction of the flag predicates
+__global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __restrict__ lists, int* __restrict__ counts) {
+    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (l >= NLISTS) return;
+    if (l == L_INIT) { if (lane == 0) counts[L_INIT] = 0; return; }
+    int n = 0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int b = b0 + lane;
+        const int f = (b < B) ? flags[b] : 0;
+        bool p = (f & RC_F_ACTIVE) != 0;
+        if (l == L_HI) p = p && (f & RC_F_HI);
+        else if (l == L_6A) p = p && (f & RC_F_FIRST_FRAME);
+        else if (l == L_6B) p = p && (f & RC_F_R6B);
+        else if (l == L_LATE) p = p && (f & RC_F_LATE);
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if (p) lists[l * B + n + __popc(m & ((1u << lane) - 1u))] = b;
+        n += __popc(m);
+    }
+    if (lane == 0) counts[l] = n;
+}
+
+__global__ void __launch_bounds__(128) rc_mid_kernel(const int* __restrict__ flags, int B, const float* __restrict__ rcr,
+                                                      const float* __restrict__ lerpw, const float* X3, const float* X6, float* X7) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int f = flags[b];
+    if (!(f & RC_F_ACTIVE)) return;
+    float r[9];
+    for (int i = 0; i < 9; ++i) r[i] = rcr[b * 9 + i];
+    rc_mid_row(f, r, lerpw + b * 2, X3 + (size_t)b * RC_K3 + 72, X6 + (size_t)b * RC_K6 + 171, X7 + (size_t)b * RC_K7 + 72);
+}
+
+__global__ void __launch_bounds__(64) rc_kin_kernel(RcNetCfg cfg, const RcModelConst* __restrict__ M, RcRowState* rows,
+                                                     const int* __restrict__ flags, int B, StepIO io,
+                                                     const float* __restrict__ Y7, const float* __restrict__ Y8,
+                                                     const float* __restrict__ Y3, const float* __restrict__ Y6,
+                                                     const float* __restrict__ rcr, const float* __restrict__ conf,
+                                                     const float* __restrict__ gravity_all, float* X4, float* X6,
+                                                     const float* X7, float* XI, int* lists, int* counts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int f = flags[b];
+    if (!(f & RC_F_ACTIVE)) return;
+    const int t = io.d_t ? *io.d_t : 0;
+    float y7[144], r[9], g[3], ft[3] = {0.f, 0.f, 0.f}, pose[216], tran[3];
+    for (int i = 0; i < 144; ++i) y7[i] = Y7[(size_t)b * 144 + i];
+    for (int i = 0; i < 9; ++i) r[i] = rcr[b * 9 + i];
+    const float* gp = io.gravity ? (io.gravity + (size_t)b * 3) : gravity_all;
+    for (int i = 0; i < 3; ++i) g[i] = gp[i];
+    if (f & RC_F_FIRST_TRAN) for (int i = 0; i < 3; ++i) ft[i] = io.first_tran[(size_t)b * 3 + i];
+    RcRowState st = rows[b];
+    const int need_init = rc_kin_row(cfg, *M, &st, f, y7, Y8 + b * 4, Y3 + b * 4, Y6 + b * 4, r, conf[b], g, ft, pose, tran,
+                                     X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6);
+    rows[b] = st;
+    float* po = io.pose + b * io.sp + (long long)t * 216;
+    float* to = io.tran + b * io.st + (long long)t * 3;
+    for (int i = 0; i < 216; ++i) po[i] = pose[i];
+    for (int i = 0; i < 3; ++i) to[i] = tran[i];
+    if (need_init) {
+        for (int i = 0; i < 69; ++i) XI[(size_t)b * kInitK0 + i] = X7[(size_t)b * RC_K7 + 72 + i];
+        for (int i = 69; i < kInitK0; ++i) XI[(size_t)b * kInitK0 + i] = 0.f;
+        lists[L_INIT * B + atomicAdd(&counts[L_INIT], 1)] = b;
+    }
+}
+
+// init_net output [h0 | h1 | c0 | c1] -> rnn2 state (sig_mp.py:182-183)
+__global__ void __launch_bounds__(256) rc_init_scatter_kernel(const float* __restrict__ I3, const int* __restrict__ rows,
+                                                               const int* __restrict__ count, float* h0, float* h1, float* c0, float* c1) {
+    const int cnt = *count;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)cnt * 2048; e += (long long)gridDim.x * blockDim.x) {
+        const int r = rows[e / 2048], q = (int)(e % 2048), u = q & 511;
+        const float v = I3[(size_t)r * 2048 + q];
+        float* dst = (q < 512) ? h0 : (q < 1024 ? h1 : (q < 1536 ? c0 : c1));
+        dst[(size_t)r * 512 + u] = v;
+    }
+}
+
+__global__ void rc_advance_kernel(int* d_t) { *d_t += 1; }
+__global__ void rc_reset_rows_kernel(RcRowState* rows, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) rc_row_state_reset(&rows[b]);
+}
+
+// ---- host helpers ------------------------------------------------------------------------------------------------
+template <class T>
+int dev_alloc(std::vector<void*>& pool, T** p, size_t n) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, (n ? n : 1) * sizeof(T));
+    if (e != cudaSuccess) { rc_set_error("cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e)); return RC_ERR_ALLOC; }
+    pool.push_back(q);
+    *p = (T*)q;
+    return RC_OK;
+}
+#define RC_TRY(x) do { int rc_ = (x); if (rc_ != RC_OK) return rc_; } while (0)
+
+int upload(std::vector<void*>& pool, float** d, const std::vector<float>& h) {
+    RC_TRY(dev_alloc(pool, d, h.size()));
+    RC_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return RC_OK;
+}
+
+int launch_linear(const RcLinear& a, int B, bool lstm, void* stream) {
+    if (B <= 8) {
+        const int njobs = a.Nw / 4;
+        const int K = a.K1 + a.K2;
+        // enough warps to cover the SMs twice, but never split a K shorter than one warp pass
+        int ksplit = 1;
+        while (ksplit < 8 && njobs * ksplit < 2 * 148 * 8 && K / (ksplit * 2) >= 128) ksplit *= 2;
+        const int jpb = 8 / ksplit;
+        const int grid = rc_cdiv(njobs, jpb);
+#define RC_GEMV(MM)                                                                          \
+        if (lstm) RC_LAUNCH((rc_gemv_kernel<MM, true>), grid, 256, 0, stream, a, ksplit);    \
+        else RC_LAUNCH((rc_gemv_kernel<MM, false>), grid, 256, 0, stream, a, ksplit)
+        if (B == 1) { RC_GEMV(1); }
+        else if (B == 2) { RC_GEMV(2); }
+        else if (B <= 4) { RC_GEMV(4); }
+        else { RC_GEMV(8); }
+#undef RC_GEMV
+    } else {
+        dim3 grid(rc_cdiv(a.Nw, kBN), rc_cdiv(B, kBM));
+        if (lstm) RC_LAUNCH((rc_gemm_kernel<true>), grid, 256, 0, stream, a);
+        else RC_LAUNCH((rc_gemm_kernel<false>), grid, 256, 0, stream, a);
+    }
+    RC_CHECK_LAUNCH();
+    return RC_OK;
+}
+
+// one sub-net over the rows of list `li`: X [B, K1] -> (optional) Y
+int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, void* stream) {
+    const NetDev& w = s->net->nets[ni];
+    NetBuf& nb = s->nb[ni];
+    const int B = s->B;
+    const int* rows = s->lists + (size_t)li * B;
+    const int* count = s->counts + li;
+    RcLinear a;
+    memset(&a, 0, sizeof(a));
+    a.rows = rows; a.count = count;
+    // linear1 + relu
+    a.X = X; a.ldx = w.K1; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.K1; a.K2 = 0;
+    a.W = w.W1; a.bias = w.b1; a.N = w.H; a.Nw = w.H; a.Y = nb.a1; a.ldy = w.H; a.relu = 1; a.H = w.H;
+    RC_TRY(launch_linear(a, B, false, stream));
+    // LSTM layers
+    for (int l = 0; l < 2; ++l) {
+        a.X = (l == 0) ? nb.a1 : nb.hn[0]; a.ldx = w.H; a.X2 = nb.h[l]; a.ldx2 = w.H; a.K1 = w.H; a.K2 = w.H;
+        a.W = w.WL[l]; a.bias = w.bL[l]; a.N = 4 * w.H; a.Nw = 4 * w.H; a.Y = nullptr; a.ldy = 0; a.relu = 0;
+        a.C = nb.c[l]; a.Hout = nb.hn[l];
+        RC_TRY(launch_linear(a, B, true, stream));
+    }
+    {
+        const long long work = (long long)B * (w.H / 4);
+        const int grid = (int)std::min<long long>(rc_cdiv(work, 256), 1184);
+        RC_LAUNCH(rc_commit_kernel, grid, 256, 0, stream, nb.hn[0], nb.hn[1], nb.h[0], nb.h[1], w.H, rows, count);
+        RC_CHECK_LAUNCH();
+    }
+    if (Y) {
+        a.X = nb.hn[1]; a.ldx = w.H; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.H; a.K2 = 0;
+        a.W = w.W2; a.bias = w.b2; a.N = w.out; a.Nw = w.out4; a.Y = Y; a.ldy = ldy; a.relu = 0; a.C = nullptr; a.Hout = nullptr;
+        RC_TRY(launch_linear(a, B, false, stream));
+    }
+    return RC_OK;
+}
+
+int init_pass(rc_state* s, void* stream) {
+    const rc_net* n = s->net;
+    const int B = s->B;
+    RcLinear a;
+    memset(&a, 0, sizeof(a));
+    a.rows = s->lists + (size_t)L_INIT * B; a.count = s->counts + L_INIT;
+    const float* xin[3] = {s->XI, s->I1, s->I2};
+    float* yout[3] = {s->I1, s->I2, s->I3};
+    const int kin[3] = {kInitK0, 512, 1024};
+    for (int l = 0; l < 3; ++l) {
+        a.X = xin[l]; a.ldx = kin[l]; a.K1 = kin[l]; a.K2 = 0; a.X2 = nullptr;
+        a.W = n->Wi[l]; a.bias = n->bi[l]; a.N = kInitDims[l + 1]; a.Nw = kInitDims[l + 1];
+        a.Y = yout[l]; a.ldy = kInitDims[l + 1]; a.relu = (l < 2); a.H = 0;
+        RC_TRY(launch_linear(a, B, false, stream));
+    }
+    const NetBuf& nb = s->nb[NET2];
+    RC_LAUNCH(rc_init_scatter_kernel, std::min(rc_cdiv((long long)B * 2048, 256), 1184), 256, 0, stream, s->I3,
+              s->lists + (size_t)L_INIT * B, s->counts + L_INIT, nb.h[0], nb.h[1], nb.c[0], nb.c[1]);
+    RC_CHECK_LAUNCH();
+    return RC_OK;
+}
+
+int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advance, void* stream) {
+    const rc_net* n = s->net;
+    const int B = s->B;
+    RC_LAUNCH(rc_prep_kernel, rc_cdiv(B, 128), 128, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4, s->X6, s->X7,
+              s->rcr, s->conf, s->lerpw, s->flags);
+    RC_CHECK_LAUNCH();
+    RC_LAUNCH(rc_lists_kernel, 1, NLISTS * 32, 0, stream, s->flags, B, s->lists, s->counts);
+    RC_CHECK_LAUNCH();
+    RC_TRY(net_pass(s, NET2, L_ALL, s->X2, s->X3 + 72, RC_K3, stream));                 // j3dr_i            (:144)
+    RC_TRY(net_pass(s, NET3, L_ALL, s->X3, s->Y3, 4, stream));                         // vr                (:145)
+    RC_TRY(net_pass(s, NET4, L_HI, s->X4, s->X6 + 171, RC_K6, stream));                // j3dc              (:153)
+    if (any_first_frame) RC_TRY(net_pass(s, NET6, L_6A, s->X6, s->Y6, 4, stream));     // pc on first_frame (:156)
+    RC_TRY(net_pass(s, NET6, L_6B, s->X6, s->Y6, 4, stream));                          // pc                (:161,165)
+    RC_LAUNCH(rc_mid_kernel, rc_cdiv(B, 128), 128, 0, stream, s->flags, B, s->rcr, s->lerpw, s->X3, s->X6, s->X7);
+    RC_CHECK_LAUNCH();
+    RC_TRY(net_pass(s, NET7, L_ALL, s->X7, s->Y7, 144, stream));                       // poseg6d           (:169)
+    RC_TRY(net_pass(s, NET8, L_ALL, s->X7, s->Y8, 4, stream));                         // contact logits    (:170)
+    RC_LAUNCH(rc_kin_kernel, rc_cdiv(B, 64), 64, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B, io, s->Y7, s->Y8,
+              s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
+    RC_CHECK_LAUNCH();
+    RC_TRY(init_pass(s, stream));                                                      // (:178-183)
+    RC_TRY(net_pass(s, NET6, L_LATE, s->X6, nullptr, 0, stream));                      // vision updater    (:267)
+    RC_TRY(net_pass(s, NET4, L_LATE, s->X4, nullptr, 0, stream));                      //                   (:271)
+    if (advance) { RC_LAUNCH(rc_advance_kernel, 1, 1, 0, stream, s->d_t); RC_CHECK_LAUNCH(); }
+    return RC_OK;
+}
+
+// ---- weight packing (host) ------------------------------------------------------------------------------------
+const std::vector<float>* get_staged(rc_net* n, const std::string& key, size_t numel) {
+    auto it = n->staging.find(key);
+    if (it == n->staging.end()) { rc_set_error("rc_net_finalize: missing tensor %s", key.c_str()); return nullptr; }
+    if (it->second.size() != numel) { rc_set_error("rc_net_finalize: %s has %zu elements, expected %zu", key.c_str(), it->second.size(), numel); return nullptr; }
+    return &it->second;
+}
+
+int pack_linear(rc_net* n, const std::string& prefix, int out, int in, int out_pad, int in_pad, float** dW, float** db) {
+    const std::vector<float>* w = get_staged(n, prefix + ".weight", (size_t)out * in);
+    const std::vector<float>* b = get_staged(n, prefix + ".bias", (size_t)out);
+    if (!w || !b) return RC_ERR_STATE;
+    std::vector<float> pw, pb;
+    rc_pack_linear(w->data(), b->data(), out, in, out_pad, in_pad, pw, pb);
+    RC_TRY(upload(n->allocs, dW, pw));
+    RC_TRY(upload(n->allocs, db, pb));
+    n->weight_bytes += (int64_t)(pw.size() + pb.size()) * 4;
+    return RC_OK;
+}
+
+int pack_lstm(rc_net* n, const std::string& prefix, int layer, int H, float** dW, float** db) {
+    const std::string sfx = "_l" + std::to_string(layer);
+    const std::vector<float>* wih = get_staged(n, prefix + ".rnn.weight_ih" + sfx, (size_t)4 * H * H);
+    const std::vector<float>* whh = get_staged(n, prefix + ".rnn.weight_hh" + sfx, (size_t)4 * H * H);
+    const std::vector<float>* bih = get_staged(n, prefix + ".rnn.bias_ih" + sfx, (size_t)4 * H);
+    const std::vector<float>* bhh = get_staged(n, prefix + ".rnn.bias_hh" + sfx, (size_t)4 * H);
+    if (!wih || !whh || !bih || !bhh) return RC_ERR_STATE;
+    std::vector<float> pw, pb;
+    rc_pack_lstm(wih->data(), whh->data(), bih->data(), bhh->data(), H, pw, pb);
+    RC_TRY(upload(n->allocs, dW, pw));
+    RC_TRY(upload(n->allocs, db, pb));
+    n->weight_bytes += (int64_t)(pw.size() + pb.size()) * 4;
+    return RC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void rc_net_default_config(rc_net_config* c, int live) {
+    if (!c) return;
+    c->conf_lo = live ? 0.85 : 0.7;
+    c->conf_hi = live ? 0.9 : 0.8;
+    c->tran_filter_num = live ? 0.01 : 0.05;
+    c->contact_threshold = 0.7f;
+    c->height_threshold = 0.15f;
+    c->distance_threshold = 10.f;
+    c->use_flat_floor = 1;
+    c->live = live ? 1 : 0;
+    c->update_vision_freq = 30;
+}
+
+static void apply_cfg(rc_net* n, const rc_net_config* c) {
+    n->cfg.conf_lo = c->conf_lo; n->cfg.conf_hi = c->conf_hi; n->cfg.tran_filter = c->tran_filter_num;
+    n->cfg.contact_thr = c->contact_threshold; n->cfg.height_thr = c->height_threshold; n->cfg.dist_thr = c->distance_threshold;
+    n->cfg.use_flat_floor = c->use_flat_floor; n->cfg.live = c->live; n->cfg.update_vision_freq = c->update_vision_freq;
+}
+
+int rc_net_create(rc_net** out, const rc_model* model, const rc_net_config* cfg) {
+    RC_ARG(out && model);
+    rc_net* n = new rc_net();
+    n->model = model;
+    rc_net_config def;
+    rc_net_default_config(&def, 0);
+    apply_cfg(n, cfg ? cfg : &def);
+    *out = n;
+    return RC_OK;
+}
+
+int rc_net_set_config(rc_net* n, const rc_net_config* cfg) {
+    RC_ARG(n && cfg);
+    apply_cfg(n, cfg);
+    return RC_OK;
+}
+
+void rc_net_destroy(rc_net* n) {
+    if (!n) return;
+    for (void* p : n->allocs) cudaFree(p);
+    delete n;
+}
+
+int rc_net_set_tensor(rc_net* n, const char* key, const float* data, int64_t numel) {
+    RC_ARG(n && key && data && numel > 0);
+    if (n->finalized) { rc_set_error("rc_net_set_tensor after rc_net_finalize"); return RC_ERR_STATE; }
+    n->staging[key].assign(data, data + numel);
+    return RC_OK;
+}
+
+int rc_net_finalize(rc_net* n) {
+    RC_ARG(n);
+    if (n->finalized) return RC_OK;
+    for (int i = 0; i < NNETS; ++i) {
+        NetDev& d = n->nets[i];
+        d.in = kNetIn[i]; d.K1 = kNetK1[i]; d.H = kNetH[i]; d.out = kNetOut[i]; d.out4 = (d.out + 3) / 4 * 4;
+        const std::string p = "rnn" + std::to_string(kNetId[i]);
+        RC_TRY(pack_linear(n, p + ".linear1", d.H, d.in, d.H, d.K1, &d.W1, &d.b1));
+        for (int l = 0; l < 2; ++l) RC_TRY(pack_lstm(n, p, l, d.H, &d.WL[l], &d.bL[l]));
+        RC_TRY(pack_linear(n, p + ".linear2", d.out, d.H, d.out4, d.H, &d.W2, &d.b2));
+    }
+    const int64_t per_frame = n->weight_bytes;
+    const int kin[3] = {kInitK0, 512, 1024};
+    for (int l = 0; l < 3; ++l)
+        RC_TRY(pack_linear(n, "rnn2.init_net." + std::to_string(2 * l), kInitDims[l + 1], kInitDims[l], kInitDims[l + 1], kin[l], &n->Wi[l], &n->bi[l]));
+    n->weight_bytes = per_frame;
+    n->staging.clear();
+    n->finalized = true;
+    return RC_OK;
+}
+
+int64_t rc_net_weight_bytes(const rc_net* n) { return n ? n->weight_bytes : 0; }
+
+int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
+    RC_ARG(out && net && B > 0);
+    if (!net->finalized) { rc_set_error("rc_state_create: net not finalized"); return RC_ERR_STATE; }
+    rc_state* s = new rc_state();
+    s->net = net; s->B = B;
+    int rc = RC_OK;
+    auto A = [&](float** p, size_t n) { if (rc == RC_OK) rc = dev_alloc(s->allocs, p, n); };
+    for (int i = 0; i < NNETS; ++i) {
+        const size_t n = (size_t)B * net->nets[i].H;
+        for (int l = 0; l < 2; ++l) { A(&s->nb[i].h[l], n); A(&s->nb[i].c[l], n); A(&s->nb[i].hn[l], n); }
+        A(&s->nb[i].a1, n);
+    }
+    A(&s->X2, (size_t)B * RC_K2); A(&s->X3, (size_t)B * RC_K3); A(&s->X4, (size_t)B * RC_K4); A(&s->X6, (size_t)B * RC_K6);
+    A(&s->X7, (size_t)B * RC_K7); A(&s->XI, (size_t)B * kInitK0);
+    A(&s->Y3, (size_t)B * 4); A(&s->Y6, (size_t)B * 4); A(&s->Y7, (size_t)B * 144); A(&s->Y8, (size_t)B * 4);
+    A(&s->I1, (size_t)B * 512); A(&s->I2, (size_t)B * 1024); A(&s->I3, (size_t)B * 2048);
+    A(&s->rcr, (size_t)B * 9); A(&s->conf, (size_t)B); A(&s->lerpw, (size_t)B * 2); A(&s->gravity, 4);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->flags, (size_t)B);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->lists, (size_t)NLISTS * B);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->counts, (size_t)NLISTS);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->d_t, (size_t)1);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->rows, (size_t)B);
+    if (rc != RC_OK) { rc_state_destroy(s); return rc; }
+    const float g[4] = {-0.0029f, 0.9980f, -0.0273f, 0.f};     // Net.gravityc default (sig_mp.py:36)
+    cudaError_t e = cudaMemcpy(s->gravity, g, sizeof(g), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { rc_set_error("rc_state_create: %s", cudaGetErrorString(e)); rc_state_destroy(s); return RC_ERR_CUDA; }
+    rc = rc_state_reset(s, nullptr);
+    if (rc == RC_OK && cudaDeviceSynchronize() != cudaSuccess) rc = RC_ERR_CUDA;
+    if (rc != RC_OK) { rc_state_destroy(s); return rc; }
+    *out = s;
+    return RC_OK;
+}
+
+void rc_state_destroy(rc_state* s) {
+    if (!s) return;
+    if (s->graph) cudaGraphExecDestroy(s->graph);
+    for (void* p : s->allocs) cudaFree(p);
+    cudaFree(s->hj); cudaFree(s->ha); cudaFree(s->ho); cudaFree(s->hp); cudaFree(s->ht); cudaFree(s->hft);
+    cudaFree(s->hlen); cudaFree(s->hfl);
+    delete s;
+}
+
+int rc_state_reset(rc_state* s, void* stream) {
+    RC_ARG(s);
+    cudaStream_t st = (cudaStream_t)stream;
+    const rc_net* n = s->net;
+    for (int i = 0; i < NNETS; ++i) {
+        const size_t bytes = (size_t)s->B * n->nets[i].H * sizeof(float);
+        for (int l = 0; l < 2; ++l) {
+            RC_CUDA(cudaMemsetAsync(s->nb[i].h[l], 0, bytes, st));
+            RC_CUDA(cudaMemsetAsync(s->nb[i].c[l], 0, bytes, st));
+            RC_CUDA(cudaMemsetAsync(s->nb[i].hn[l], 0, bytes, st));
+        }
+    }
+    RC_CUDA(cudaMemsetAsync(s->Y3, 0, (size_t)s->B * 4 * sizeof(float), st));
+    RC_CUDA(cudaMemsetAsync(s->Y6, 0, (size_t)s->B * 4 * sizeof(float), st));
+    RC_CUDA(cudaMemsetAsync(s->X6, 0, (size_t)s->B * RC_K6 * sizeof(float), st));
+    RC_CUDA(cudaMemsetAsync(s->X4, 0, (size_t)s->B * RC_K4 * sizeof(float), st));
+    RC_CUDA(cudaMemsetAsync(s->d_t, 0, sizeof(int), st));
+    RC_LAUNCH(rc_reset_rows_kernel, rc_cdiv(s->B, 128), 128, 0, stream, s->rows, s->B);
+    RC_CHECK_LAUNCH();
+    return RC_OK;
+}
+
+int rc_state_set_gravity(rc_state* s, const float* g, void* stream) {
+    RC_ARG(s && g);
+    RC_CUDA(cudaMemcpyAsync(s->gravity, g, 3 * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    RC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return RC_OK;
+}
+
+int rc_forward_step(rc_state* s, const float* j2dc, const float* accc, const float* oric, const float* gravity,
+                    const float* first_tran, const int32_t* row_flags, int any_first_frame, float* pose, float* tran,
+                    void* stream) {
+    RC_ARG(s && j2dc && accc && oric && pose && tran);
+    StepIO io;
+    io.j2dc = j2dc; io.accc = accc; io.oric = oric; io.sj = 99; io.sa = 18; io.so = 54;
+    io.gravity = gravity; io.first_tran = first_tran; io.row_flags = row_flags; io.lengths = nullptr;
+    io.pose = pose; io.tran = tran; io.sp = 216; io.st = 3; io.d_t = nullptr; io.first_mode = 1;
+    return enqueue_step(s, io, any_first_frame, false, stream);
+}
+
+int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* accc, const float* oric,
+                        const int32_t* lengths, const float* gravity, const float* first_tran, const int32_t* row_flags,
+                        int any_first_frame, float* pose, float* tran, int use_graph, void* stream) {
+    RC_ARG(s && T >= 0);
+    if (T == 0) return RC_OK;
+    RC_ARG(j2dc && accc && oric && pose && tran);
+    cudaStream_t st = (cudaStream_t)stream;
+    RC_TRY(rc_state_reset(s, stream));
+    StepIO io;
+    io.j2dc = j2dc; io.accc = accc; io.oric = oric;
+    io.sj = (long long)T * 99; io.sa = (long long)T * 18; io.so = (long long)T * 54;
+    io.gravity = gravity; io.first_tran = first_tran; io.row_flags = row_flags; io.lengths = lengths;
+    io.pose = pose; io.tran = tran; io.sp = (long long)T * 216; io.st = (long long)T * 3;
+    io.d_t = s->d_t; io.first_mode = 2;
+    RC_TRY(enqueue_step(s, io, any_first_frame, true, stream));
+    if (T == 1) return RC_OK;
+    if (!use_graph) {
+        for (int t = 1; t < T; ++t) RC_TRY(enqueue_step(s, io, 0, true, stream));
+        return RC_OK;
+    }
+    std::vector<const void*> key = {j2dc, accc, oric, lengths, gravity, first_tran, row_flags, pose, tran,
+                                    (const void*)(intptr_t)T, (const void*)stream};
+    if (!s->graph || key != s->graph_key) {
+        if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+        cudaGraph_t g = nullptr;
+        RC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_step(s, io, 0, true, stream);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (rc != RC_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) { rc_set_error("graph capture: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
+        e = cudaGraphInstantiate(&s->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { s->graph = nullptr; rc_set_error("graph instantiate: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
+        s->graph_key = key;
+    }
+    for (int t = 1; t < T; ++t) RC_CUDA(cudaGraphLaunch(s->graph, st));
+    return RC_OK;
+}
+
+int rc_forward_sequence_host(rc_state* s, int32_t T, const float* hj, const float* ha, const float* ho,
+                             const int32_t* hlen, const float* hft, const int32_t* hfl, float* hp, float* ht,
+                             int use_graph, void* stream) {
+    RC_ARG(s && T > 0 && hj && ha && ho && hp && ht);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)s->B;
+    if (s->host_cap_T < T) {
+        cudaFree(s->hj); cudaFree(s->ha); cudaFree(s->ho); cudaFree(s->hp); cudaFree(s->ht);
+        s->hj = s->ha = s->ho = s->hp = s->ht = nullptr;
+        s->host_cap_T = 0;
+        if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+        RC_CUDA(cudaMalloc(&s->hj, B * T * 99 * sizeof(float)));
+        RC_CUDA(cudaMalloc(&s->ha, B * T * 18 * sizeof(float)));
+        RC_CUDA(cudaMalloc(&s->ho, B * T * 54 * sizeof(float)));
+        RC_CUDA(cudaMalloc(&s->hp, B * T * 216 * sizeof(float)));
+        RC_CUDA(cudaMalloc(&s->ht, B * T * 3 * sizeof(float)));
+        if (!s->hft) RC_CUDA(cudaMalloc(&s->hft, B * 3 * sizeof(float)));
+        if (!s->hlen) RC_CUDA(cudaMalloc(&s->hlen, B * sizeof(int)));
+        if (!s->hfl) RC_CUDA(cudaMalloc(&s->hfl, B * sizeof(int)));
+        s->host_cap_T = T;
+    }
+    RC_CUDA(cudaMemcpyAsync(s->hj, hj, B * T * 99 * sizeof(float), cudaMemcpyHostToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(s->ha, ha, B * T * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
+    RC_CUDA(cudaMemcpyAsync(s->ho, ho, B * T * 54 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (hft) RC_CUDA(cudaMemcpyAsync(s->hft, hft, B * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (hlen) RC_CUDA(cudaMemcpyAsync(s->hlen, hlen, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    int any_ff = 0;
+    if (hfl) {
+        RC_CUDA(cudaMemcpyAsync(s->hfl, hfl, B * sizeof(int), cudaMemcpyHostToDevice, st));
+        for (size_t b = 0; b < B; ++b) any_ff |= (hfl[b] & RC_ROW_FIRST_FRAME);
+    }
+    RC_TRY(rc_forward_sequence(s, T, s->hj, s->ha, s->ho, hlen ? s->hlen : nullptr, nullptr, hft ? s->hft : nullptr,
+                               hfl ? s->hfl : nullptr, any_ff, s->hp, s->ht, use_graph, stream));
+    RC_CUDA(cudaMemcpyAsync(hp, s->hp, B * T * 216 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RC_CUDA(cudaMemcpyAsync(ht, s->ht, B * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RC_CUDA(cudaStreamSynchronize(st));
+    return RC_OK;
+}
+
+int rc_state_debug_output(rc_state* s, int which, float* out, void* stream) {
+    RC_ARG(s && out);
+    const float* src; int ld, w;
+    switch (which) {
+        case 2: src = s->X3 + 72; ld = RC_K3; w = 69; break;
+        case 3: src = s->Y3; ld = 4; w = 3; break;
+        case 4: src = s->X6 + 171; ld = RC_K6; w = 69; break;
+        case 6: src = s->Y6; ld = 4; w = 3; break;
+        case 7: src = s->Y7; ld = 144; w = 144; break;
+        case 8: src = s->Y8; ld = 4; w = 2; break;
+        default: rc_set_error("rc_state_debug_output: which=%d", which); return RC_ERR_ARG;
+    }
+    RC_CUDA(cudaMemcpy2DAsync(out, (size_t)w * 4, src, (size_t)ld * 4, (size_t)w * 4, (size_t)s->B, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return RC_OK;
+}
+
+}  // extern "C"
