@@ -1,0 +1,256 @@
+r"""``Net`` — the RobustCap fusion network (reference ``net/sig_mp.py:23-274``) on the B200 library.
+
+Same public surface as the reference class: ``Net()``, ``forward_online(j2dc, accc, oric, first_tran=None,
+first_frame=False) -> (pose[24,3,3], tran[3])`` on the CPU, ``reset_states()``, ``load_state_dict`` with the
+reference key set, and the class-level knobs (``gravityc``, ``conf_range``, ``use_flat_floor``, ``live`` ...).
+New: ``forward_offline`` — defined as ``reset_states()`` followed by ``forward_online`` over the frames
+— for one sequence ``[T, ...]`` or a batch ``[B, T, ...]`` of independent sequences.
+
+Python only holds tensors and handles; every arithmetic step of the frame runs in CUDA kernels behind the C ABI
+(``include/robustcap_b200.h``).  There is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from .model import ParametricModel
+from .rnn import RNN, RNNWithInit
+
+__all__ = ['Net', 'get_bbox_scale', 'sync_mp3d']
+
+
+class Net(torch.nn.Module):
+    # class-level knobs, same names and defaults as net/sig_mp.py:27-45
+    hidden_size = 512
+    conf_range = (0.7, 0.8)
+    contact_threshold = 0.7
+    smooth = 1
+    use_flat_floor = True
+    use_reproj_opt = False           # reference default; the closed-form re-projection tweak (:244-261) is dead code
+    use_vision_updater = True
+    use_imu_updater = True
+    name = 'sig_mp'
+    gravityc = torch.tensor([-0.0029, 0.9980, -0.0273])
+    imu_num = 6
+    height_threhold = 0.15
+    distrance_threshold = 10
+    tran_filter_num = 0.05
+    live = False
+    update_vision_freq = 30
+
+    smpl_file = 'models/SMPL_male.pkl'   # config.paths.smpl_file
+    body_model = None                    # shared ParametricModel (the reference keeps a module-level global)
+
+    def __init__(self, body_model: ParametricModel = None):
+        super().__init__()
+        n = Net.imu_num
+        self.rnn2 = RNNWithInit(input_size=n * 3 + n * 9, output_size=23 * 3, hidden_size=Net.hidden_size, num_rnn_layer=2, dropout=0.4)
+        self.rnn3 = RNN(input_size=n * 3 + n * 9 + 23 * 3, output_size=3, hidden_size=Net.hidden_size, num_rnn_layer=2, dropout=0.4)
+        self.rnn4 = RNN(input_size=n * 3 + n * 9 + 33 * 3, output_size=23 * 3, hidden_size=1024 + 256, num_rnn_layer=2, dropout=0.4)
+        self.rnn6 = RNN(input_size=n * 3 + n * 9 + 33 * 3 + 23 * 3, output_size=3, hidden_size=1024, num_rnn_layer=2, dropout=0.4)
+        self.rnn7 = RNN(input_size=n * 3 + n * 9 + 23 * 3, output_size=24 * 6, hidden_size=512, num_rnn_layer=2, dropout=0.1)
+        self.rnn8 = RNN(input_size=n * 3 + n * 9 + 23 * 3, output_size=2, hidden_size=Net.hidden_size, num_rnn_layer=2, dropout=0.4)
+        if self.live:                                     # sig_mp.py:91-93
+            self.conf_range = (0.85, 0.9)
+            self.tran_filter_num = 0.01
+        if body_model is None:
+            if Net.body_model is None:
+                Net.body_model = ParametricModel(Net.smpl_file)
+            body_model = Net.body_model
+        self._body = body_model
+        self._net = None            # rc_net handle
+        self._states = {}           # batch size -> rc_state handle
+        self._cfg_pushed = None
+        self._grav_pushed = {}
+        self._dirty = True
+        self._use_graph = True
+
+    # ---- native plumbing -------------------------------------------------------------------------------------------
+    def _config(self):
+        c = _lib.NetConfig()
+        c.conf_lo, c.conf_hi = float(self.conf_range[0]), float(self.conf_range[1])
+        c.tran_filter_num = float(self.tran_filter_num)
+        c.contact_threshold = float(self.contact_threshold)
+        c.height_threshold = float(self.height_threhold)
+        c.distance_threshold = float(self.distrance_threshold)
+        c.use_flat_floor = int(bool(self.use_flat_floor))
+        c.live = int(bool(self.live))
+        c.update_vision_freq = int(self.update_vision_freq)
+        return c
+
+    def _release(self):
+        lib = _lib.load()
+        for h in self._states.values():
+            lib.rc_state_destroy(h)
+        self._states = {}
+        self._grav_pushed = {}
+        if self._net is not None:
+            lib.rc_net_destroy(self._net)
+            self._net = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def _ensure_native(self):
+        lib = _lib.load()
+        _lib.require_cuda()
+        if self._net is not None and not self._dirty:
+            cfg = self._config()
+            key = bytes(cfg)
+            if key != self._cfg_pushed:
+                _lib.check(lib.rc_net_set_config(self._net, ctypes.byref(cfg)))
+                self._cfg_pushed = key
+            return
+        self._release()
+        cfg = self._config()
+        h = _lib.vp()
+        _lib.check(lib.rc_net_create(ctypes.byref(h), self._body._native(), ctypes.byref(cfg)))
+        self._net = h
+        self._cfg_pushed = bytes(cfg)
+        for key, val in self.state_dict().items():
+            t = val.detach().to('cpu', torch.float32).contiguous()
+            _lib.check(lib.rc_net_set_tensor(h, key.encode(), _lib.hptr(t), t.numel()))
+        _lib.check(lib.rc_net_finalize(h))
+        self._dirty = False
+
+    def _state(self, B):
+        lib = _lib.load()
+        if B not in self._states:
+            h = _lib.vp()
+            _lib.check(lib.rc_state_create(ctypes.byref(h), self._net, B))
+            self._states[B] = h
+        g = self.gravityc.detach().to('cpu', torch.float32).reshape(3).contiguous()
+        key = tuple(g.tolist())
+        if self._grav_pushed.get(B) != key:
+            _lib.check(lib.rc_state_set_gravity(self._states[B], _lib.hptr(g), _lib.stream()))
+            self._grav_pushed[B] = key
+        return self._states[B]
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._dirty = True
+        return out
+
+    def weight_bytes(self):
+        self._ensure_native()
+        return int(_lib.load().rc_net_weight_bytes(self._net))
+
+    # ---- reference API -------------------------------------------------------------------------------------------
+    def reset_states(self):
+        r"""Reset the hidden states and the tracker variables of the online stream. sig_mp.py:95-104."""
+        if self._net is not None and 1 in self._states:
+            _lib.check(_lib.load().rc_state_reset(self._states[1], _lib.stream()))
+
+    @staticmethod
+    def cat(*x):
+        return [torch.cat(_, dim=1) for _ in zip(*x)]
+
+    @torch.no_grad()
+    def forward_online(self, j2dc, accc, oric, first_tran=None, first_frame=False):
+        r"""One frame. j2dc [33,3] (x, y on the z=1 plane, confidence), accc [6,3], oric [6,3,3] ->
+        pose [24,3,3] (local, root = pelvis IMU) and tran [3], both on the CPU. sig_mp.py:113-274."""
+        lib = _lib.load()
+        self._ensure_native()
+        dev = _lib.require_cuda()
+        st = self._state(1)
+        f32 = dict(device=dev, dtype=torch.float32)
+        dj = j2dc.detach().reshape(1, 99).to(**f32).contiguous()
+        da = accc.detach().reshape(1, 18).to(**f32).contiguous()
+        do = oric.detach().reshape(1, 54).to(**f32).contiguous()
+        flags, dft = 0, None
+        if first_frame:
+            flags |= 1
+        if first_tran is not None:
+            flags |= 2
+            dft = first_tran.detach().reshape(1, 3).to(**f32).contiguous()
+        dfl = torch.tensor([flags], dtype=torch.int32, device=dev) if flags else None
+        pose = torch.empty(1, 24, 3, 3, **f32)
+        tran = torch.empty(1, 3, **f32)
+        _lib.check(lib.rc_forward_step(st, _lib.dptr(dj), _lib.dptr(da), _lib.dptr(do), None, _lib.dptr(dft), _lib.dptr(dfl),
+                                       int(bool(first_frame)), _lib.dptr(pose), _lib.dptr(tran), _lib.stream()))
+        return pose.view(24, 3, 3).cpu(), tran.view(3).cpu()
+
+    @torch.no_grad()
+    def forward_offline(self, j2dc, accc, oric, first_tran=None, first_frame=False, lengths=None, use_graph=None,
+                        first_tran_mask=None):
+        r"""``reset_states()`` then ``forward_online`` over every frame (evaluate.py:75-85, 93), natively batched.
+
+        j2dc [T,33,3] or [B,T,33,3]; accc [..,T,6,3]; oric [..,T,6,3,3].  ``first_tran`` ([3] or [B,3]) and
+        ``first_frame`` (bool or bool[B]) apply to frame 0; ``lengths`` (int[B]) marks ragged batches (outputs beyond
+        a sequence's length are zero).  Returns pose [..,T,24,3,3], tran [..,T,3] on the device of ``j2dc``.
+        CPU inputs go through the end-to-end host entry point (H2D copy, kernels, D2H copy)."""
+        lib = _lib.load()
+        self._ensure_native()
+        dev = _lib.require_cuda()
+        single = j2dc.dim() == 3
+        if single:
+            j2dc, accc, oric = j2dc.unsqueeze(0), accc.unsqueeze(0), oric.unsqueeze(0)
+        B, T = j2dc.shape[0], j2dc.shape[1]
+        st = self._state(B)
+        use_graph = self._use_graph if use_graph is None else use_graph
+        on_cpu = not j2dc.is_cuda
+        where = dict(device='cpu' if on_cpu else dev, dtype=torch.float32)
+        j = j2dc.detach().reshape(B, T, 99).to(**where).contiguous()
+        a = accc.detach().reshape(B, T, 18).to(**where).contiguous()
+        o = oric.detach().reshape(B, T, 54).to(**where).contiguous()
+        ft = None
+        if first_tran is not None:
+            ft = first_tran.detach().reshape(-1, 3).to(**where).expand(B, 3).contiguous()
+        ff = torch.as_tensor(first_frame).reshape(-1).to(torch.int32).expand(B) if not isinstance(first_frame, bool) \
+            else torch.full((B,), int(first_frame), dtype=torch.int32)
+        ftm = torch.full((B,), 2 if ft is not None else 0, dtype=torch.int32)
+        if first_tran_mask is not None and ft is not None:     # per-sequence: which rows really pass first_tran
+            ftm = torch.as_tensor(first_tran_mask).reshape(B).to(torch.int32).cpu() * 2
+        flags = (ff.cpu() | ftm).to(torch.int32).contiguous()
+        any_ff = int(bool((flags & 1).any()))
+        use_flags = bool(flags.any())
+        ln = None if lengths is None else torch.as_tensor(lengths).to('cpu', torch.int32).reshape(B).contiguous()
+        pose = torch.zeros(B, T, 24, 3, 3, **where)
+        tran = torch.zeros(B, T, 3, **where)
+        if on_cpu:
+            _lib.check(lib.rc_forward_sequence_host(st, T, _lib.hptr(j), _lib.hptr(a), _lib.hptr(o),
+                                                    _lib.hptr(ln), _lib.hptr(ft),
+                                                    _lib.hptr(flags) if use_flags else None, _lib.hptr(pose), _lib.hptr(tran),
+                                                    int(use_graph), _lib.stream()))
+        else:
+            dflags = flags.to(dev) if use_flags else None
+            dln = None if ln is None else ln.to(dev)
+            _lib.check(lib.rc_forward_sequence(st, T, _lib.dptr(j), _lib.dptr(a), _lib.dptr(o), _lib.dptr(dln), None,
+                                               _lib.dptr(ft), _lib.dptr(dflags), any_ff, _lib.dptr(pose), _lib.dptr(tran),
+                                               int(use_graph), _lib.stream()))
+            self._keepalive = (j, a, o, ft, dflags, dln)   # kernels are still in flight
+        if single:
+            return pose[0], tran[0]
+        return pose, tran
+
+    def debug_outputs(self, B=1):
+        """Sub-net outputs of the last frame (tests): dict {2: [B,69], 3: [B,3], 4: [B,69], 6: [B,3], 7: [B,144], 8: [B,2]}."""
+        lib = _lib.load()
+        out = {}
+        for k, w in ((2, 69), (3, 3), (4, 69), (6, 3), (7, 144), (8, 2)):
+            t = torch.empty(B, w)
+            _lib.check(lib.rc_state_debug_output(self._states[B], k, _lib.hptr(t), _lib.stream()))
+            out[k] = t
+        return out
+
+
+def get_bbox_scale(uv):
+    r"""max(bbox width, bbox height) over the key-point axis. sig_mp.py:277-284 (tensor plumbing)."""
+    u_max, u_min = uv[..., 0].max(dim=-1).values, uv[..., 0].min(dim=-1).values
+    v_max, v_min = uv[..., 1].max(dim=-1).values, uv[..., 1].min(dim=-1).values
+    return torch.max(u_max - u_min, v_max - v_min)
+
+
+def sync_mp3d(vert, joint):
+    r"""33 MediaPipe points from SMPL vertices and joints. sig_mp.py:287-299 (index gather, bit-exact tables)."""
+    from .constants import MP_MASK
+    syn_3d = vert[torch.tensor(MP_MASK, device=vert.device)]
+    syn_3d[11:17] = joint[16:22].clone()
+    syn_3d[23:25] = joint[1:3].clone()
+    syn_3d[25:27] = joint[4:6].clone()
+    syn_3d[27:29] = joint[7:9].clone()
+    return syn_3d

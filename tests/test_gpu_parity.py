@@ -1,0 +1,246 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against
+(a) the committed golden vectors produced by the unmodified reference and (b) the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): joint indexing bit-exact, pose <= 1e-4 rad (geodesic), positions <= 1 mm.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from robustcap_b200 import synthetic
+from test_oracle_golden import ONLINE_CASES, load, pose_angle, get_sd
+
+pytestmark = pytest.mark.gpu
+
+RAD_TOL = 1e-4
+POS_TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def rb():
+    import robustcap_b200 as rb
+    from robustcap_b200 import _lib
+    _lib.build()
+    assert torch.cuda.is_available()
+    return rb
+
+
+@pytest.fixture(scope='module')
+def body(rb, assets):
+    return rb.ParametricModel(assets['smpl_file'])
+
+
+def cuda(x):
+    return x.cuda()
+
+
+def test_rotation_conversions(rb, golden_dir):
+    M = rb.math
+    g = load(golden_dir, 'math.npz')
+    for dev in ('cuda', 'cpu'):          # CPU tensors are staged through the GPU; same kernels
+        mv = (lambda x: x.cuda()) if dev == 'cuda' else (lambda x: x)
+        def chk(a, b, tol):
+            assert a.device.type == dev
+            assert a.shape == b.shape
+            assert (a.cpu() - b).abs().max().item() <= tol
+        chk(M.r6d_to_rotation_matrix(mv(g['r6d'])), g['r6d_to_R'], 1e-6)
+        assert torch.equal(M.rotation_matrix_to_r6d(mv(g['R'])).cpu(), g['R_to_r6d'])
+        chk(M.axis_angle_to_rotation_matrix(mv(g['aa'])), g['aa_to_R'], 1e-6)
+        chk(M.batch_rodrigues(mv(g['aa'])), g['batch_rodrigues'], 1e-6)
+        chk(M.rotation_matrix_to_axis_angle(mv(g['R_noisy'])), g['R_to_aa'], 2e-6)
+        chk(M.quaternion_to_rotation_matrix(mv(g['q'])), g['q_to_R'], 1e-6)
+        chk(M.quaternion_to_axis_angle(mv(g['q'])), g['q_to_aa'], 1e-5)
+        chk(M.axis_angle_to_quaternion(mv(g['aa'])), g['aa_to_q'], 1e-6)
+        chk(M.quaternion_product(mv(g['q']), mv(g['q2'])), g['q_prod'], 1e-6)
+        chk(M.angle_between(mv(g['R'][:32]), mv(g['R'][32:])), g['angle_between'], 1e-5)
+    assert M.r6d_to_rotation_matrix(torch.zeros(0, 6).cuda()).shape == (0, 3, 3)        # empty input
+    # ragged size (not a multiple of the 128-item block) and a large one: round trip R -> aa -> R
+    gen = torch.Generator().manual_seed(1)
+    R = synthetic._random_rotations(100003, gen).cuda()
+    R2 = M.axis_angle_to_rotation_matrix(M.rotation_matrix_to_axis_angle(R))
+    assert (R2 - R).abs().max().item() < 5e-6
+
+
+def test_tree_kinematics(rb, body, golden_dir):
+    g = load(golden_dir, 'kinematics.npz')
+    c = lambda k: g[k].cuda()
+    close = lambda a, b, tol: (a.shape == b.shape) and (a.cpu() - b).abs().max().item() <= tol
+    assert close(body.forward_kinematics_R(c('pose')), g['fk_R'], 1e-6)
+    assert close(body.inverse_kinematics_R(c('fk_R')), g['ik_R'], 1e-6)
+    assert close(body.forward_kinematics_T(c('T_local')), g['fk_T'], 1e-6)
+    assert close(body.inverse_kinematics_T(c('fk_T')), g['ik_T'], 1e-5)
+    assert close(body.joint_position_to_bone_vector(c('zero_j').unsqueeze(0)), g['bone'], 0)
+    assert close(body.bone_vector_to_joint_position(c('bone')), g['bone_to_joint'], 0)
+    # FK then IK is the identity on 4097 random frames (ragged vs the 32-frame blocks)
+    gen = torch.Generator().manual_seed(2)
+    P = synthetic._random_rotations(4097 * 24, gen).view(4097, 24, 3, 3).cuda()
+    assert (body.inverse_kinematics_R(body.forward_kinematics_R(P)) - P).abs().max().item() < 5e-6
+
+
+def test_smpl_forward_kinematics(rb, body, golden_dir):
+    g = load(golden_dir, 'kinematics.npz')
+    gr, gj = body.forward_kinematics(g['pose'].cuda(), tran=g['tran'].cuda())
+    assert (gr.cpu() - g['fk_grot']).abs().max() < 1e-6 and (gj.cpu() - g['fk_joint']).abs().max() < 1e-6
+    gr, gj, gv = body.forward_kinematics(g['pose'].cuda(), tran=g['tran'].cuda(), calc_mesh=True)
+    assert gv.shape == (5, 6890, 3)
+    assert (gj.cpu() - g['fk_mesh_joint']).abs().max() < POS_TOL * 1e-2
+    assert (gv[:2].cpu() - g['fk_mesh_vert']).abs().max() < 5e-6
+    joint, kp = body.keypoints33(g['pose'].cuda(), g['tran'].cuda())
+    assert (kp.cpu() - g['fk_mesh_vert_mp']).abs().max() < 5e-6
+    # index tables: the 33 key points must be exactly the gathered vertices / joints of the full mesh path
+    from robustcap_b200.net import sync_mp3d
+    for b in range(5):
+        ref = sync_mp3d(gv[b], gj[b])
+        assert (kp[b] - ref).abs().max() < 2e-6
+    # shaped body
+    gr, gj, gv = body.forward_kinematics(g['pose'][:2].cuda(), shape=g['shape'][:2].cuda(), tran=g['tran'][:2].cuda(), calc_mesh=True)
+    assert (gj.cpu() - g['fk_shape_joint']).abs().max() < 5e-6
+    assert (gv.cpu() - g['fk_shape_vert']).abs().max() < 5e-6
+
+
+_NETS = {}
+
+
+def get_net(rb, body, wseed, variant):
+    key = (wseed, variant)
+    if key not in _NETS:
+        net = rb.Net(body)
+        net.load_state_dict(get_sd(wseed, variant))
+        _NETS[key] = net
+    return _NETS[key]
+
+
+def start_kwargs(start):
+    if start == 'first_frame':
+        return {'first_frame': True}
+    if start == 'first_tran':
+        return {'first_tran': torch.tensor([0., 0., 4.])}
+    return {}
+
+
+@pytest.mark.parametrize('case', ONLINE_CASES, ids=[c[0] for c in ONLINE_CASES])
+def test_forward_online_golden(rb, body, golden_dir, case):
+    """Streaming B=1 (GEMV kernels), frame by frame through Net.forward_online, vs the reference's outputs."""
+    name, wseed, variant, conf, iseed, start, Tn = case
+    g = load(golden_dir, 'online_%s.npz' % name)
+    net = get_net(rb, body, wseed, variant)
+    rb.Net.gravityc = g['gravity'].clone()
+    net.reset_states()
+    poses, trans = [], []
+    rec = []
+    for t in range(Tn):
+        kw = start_kwargs(start) if t == 0 else {}
+        p, tr = net.forward_online(g['j2dc'][t], g['accc'][t], g['oric'][t], **kw)
+        assert p.device.type == 'cpu' and p.shape == (24, 3, 3) and tr.shape == (3,)
+        poses.append(p)
+        trans.append(tr)
+        if t == 0:
+            rec = net.debug_outputs(1)
+    net.reset_states()
+    # first frame: every sub-net output the reference recorded (tells which net diverges if something is off)
+    seen = {}
+    for k, o in zip(g['rec_net'].tolist(), g['rec_out']):
+        seen.setdefault(k, o)
+    for k in (2, 3, 7, 8):
+        w = rec[k].shape[1]
+        assert (rec[k][0] - seen[k][:w]).abs().max().item() < 2e-5, k
+    ang = pose_angle(torch.stack(poses), g['pose']).max().item()
+    terr = (torch.stack(trans) - g['tran']).abs().max().item()
+    assert ang < RAD_TOL, ang
+    assert terr < POS_TOL, terr
+
+
+@pytest.mark.parametrize('variant', ['default', 'contact'])
+def test_forward_offline_batched_golden(rb, body, golden_dir, variant):
+    """Batched forward_offline (tiled GEMM kernels, B > 8), ragged lengths, per-row start modes, vs the reference."""
+    cases = [c for c in ONLINE_CASES if c[2] == variant]
+    cases = cases * (12 // len(cases) + 1)
+    cases = cases[:12]
+    gs = [load(golden_dir, 'online_%s.npz' % c[0]) for c in cases]
+    Tmax = max(c[6] for c in cases)
+    B = len(cases)
+    j = torch.zeros(B, Tmax, 33, 3); a = torch.zeros(B, Tmax, 6, 3); o = torch.eye(3).expand(B, Tmax, 6, 3, 3).clone()
+    for b, (c, g) in enumerate(zip(cases, gs)):
+        T = c[6]
+        j[b, :T], a[b, :T], o[b, :T] = g['j2dc'], g['accc'], g['oric']
+    lengths = torch.tensor([c[6] for c in cases], dtype=torch.int32)
+    ff = torch.tensor([c[5] == 'first_frame' for c in cases])
+    ftm = torch.tensor([c[5] == 'first_tran' for c in cases])
+    net = get_net(rb, body, 0, variant)
+    rb.Net.gravityc = gs[0]['gravity'].clone()
+    for use_graph in (False, True):
+        pose, tran = net.forward_offline(j.cuda(), a.cuda(), o.cuda(), first_tran=torch.tensor([0., 0., 4.]), first_frame=ff,
+                                         lengths=lengths, first_tran_mask=ftm, use_graph=use_graph)
+        pose, tran = pose.cpu(), tran.cpu()
+        for b, (c, g) in enumerate(zip(cases, gs)):
+            T = c[6]
+            ang = pose_angle(pose[b, :T], g['pose']).max().item()
+            terr = (tran[b, :T] - g['tran']).abs().max().item()
+            assert ang < RAD_TOL, (c[0], use_graph, ang)
+            assert terr < POS_TOL, (c[0], use_graph, terr)
+            assert pose[b, T:].abs().max().item() == 0 if T < Tmax else True    # untouched beyond the length
+    # host-buffer entry point (the end-to-end plugin call) gives the same numbers
+    p2, t2 = net.forward_offline(j, a, o, first_tran=torch.tensor([0., 0., 4.]), first_frame=ff, lengths=lengths, first_tran_mask=ftm)
+    assert p2.device.type == 'cpu'
+    assert torch.equal(p2, pose) and torch.equal(t2, tran)
+
+
+def test_offline_vs_oracle_seeded(rb, body, assets):
+    """Seeded synthetic batch vs the CPU oracle (float32 and float64) — 24 sequences x 24 frames, all branches."""
+    from oracle.kinematics import BodyOracle
+    from oracle.fusion import FusionOracle
+    sd = get_sd(0, 'contact')
+    B, T = 24, 24
+    inp = synthetic.make_inputs(B, T, seed=77, conf='mixed')
+    net = get_net(rb, body, 0, 'contact')
+    rb.Net.gravityc = inp['gravity'].clone()
+    ff = torch.arange(B) % 2 == 0
+    pose, tran = net.forward_offline(inp['j2dc'].cuda(), inp['accc'].cuda(), inp['oric'].cuda(),
+                                     first_tran=torch.tensor([0., 0., 4.]), first_frame=ff, first_tran_mask=~ff)
+    pose, tran = pose.cpu(), tran.cpu()
+    o32 = FusionOracle(sd, BodyOracle(assets['smpl_file']))
+    o64 = FusionOracle(sd, BodyOracle(assets['smpl_file'], dtype=torch.float64), dtype=torch.float64)
+    worst = [0, 0, 0, 0]
+    for b in range(0, B, 3):
+        kw = {'first_frame': True} if ff[b] else {'first_tran': torch.tensor([0., 0., 4.])}
+        p32, t32 = o32.run(inp['j2dc'][b], inp['accc'][b], inp['oric'][b], gravity=inp['gravity'], **kw)
+        p64, t64 = o64.run(inp['j2dc'][b], inp['accc'][b], inp['oric'][b], gravity=inp['gravity'], **kw)
+        worst[0] = max(worst[0], pose_angle(pose[b], p32).max().item())
+        worst[1] = max(worst[1], (tran[b] - t32).abs().max().item())
+        worst[2] = max(worst[2], pose_angle(pose[b], p64).max().item())
+        worst[3] = max(worst[3], (tran[b].double() - t64).abs().max().item())
+    print('gpu vs oracle32: %.2e rad %.2e m; vs oracle64: %.2e rad %.2e m' % tuple(worst))
+    assert worst[0] < RAD_TOL and worst[1] < POS_TOL
+    assert worst[2] < RAD_TOL and worst[3] < POS_TOL
+
+
+def test_full_size_properties(rb, body):
+    """BASELINE.json configs[2] size (1024 sequences x 300 frames) through size-independent properties:
+    determinism (two runs bit-identical), batch invariance (a sequence gives the same result at any batch position
+    and batch size within float32 reduction-order noise), graph replay == direct launches, outputs are rotations."""
+    net = get_net(rb, body, 0, 'contact')
+    B, T = 1024, 300
+    base = synthetic.make_inputs(64, T, seed=5, conf='mixed')
+    rep = lambda x: x.repeat(B // 64, *([1] * (x.dim() - 1))).cuda()
+    j, a, o = rep(base['j2dc']), rep(base['accc']), rep(base['oric'])
+    rb.Net.gravityc = base['gravity'].clone()
+    ft = torch.tensor([0., 0., 4.])
+    p1, t1 = net.forward_offline(j, a, o, first_tran=ft)
+    p2, t2 = net.forward_offline(j, a, o, first_tran=ft)
+    assert torch.equal(p1, p2) and torch.equal(t1, t2)
+    # replicated sequences agree bit for bit wherever they sit in the batch
+    assert torch.equal(p1[:64], p1[64:128]) and torch.equal(p1[:64], p1[960:])
+    assert torch.equal(t1[:64], t1[512:576])
+    # the same sequence alone (GEMV path, different reduction order) agrees within tolerance
+    ps, ts = net.forward_offline(j[3], a[3], o[3], first_tran=ft)
+    assert pose_angle(ps.cpu(), p1[3].cpu()).max().item() < RAD_TOL
+    assert (ts - t1[3]).abs().max().item() < POS_TOL
+    # proper rotations everywhere
+    R = p1.view(-1, 3, 3)
+    err = (R.transpose(1, 2) @ R - torch.eye(3, device=R.device)).abs().max().item()
+    assert err < 1e-4, err
+    assert torch.isfinite(t1).all()
+    p3, t3 = net.forward_offline(j[:128], a[:128], o[:128], first_tran=ft, use_graph=False)
+    assert torch.equal(p3, p1[:128]) and torch.equal(t3, t1[:128])
