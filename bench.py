@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the RobustCap fusion + kinematics hot path on B200 (contract: see the task statement / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W          one JSON line (rank 0)
+  python bench.py --impl reference ...                   the reference's CPU implementation of the same path
+
+Workload (BASELINE.json configs[2]): offline evaluation of `--seqs` (1024) independent sequences x `--frames` (300)
+frames per GPU, synthetic 6-IMU + 33x3 key points with per-frame confidence U(0.6, 1.0) (all three branches of
+net/sig_mp.py:149-167), random-init weights.  One "step" = one forward_offline pass over that batch.  Multi-GPU:
+sequences are sharded by rank (weak scaling: every rank gets `--seqs` sequences), the only collective is the final
+NCCL gather of pose/tran to rank 0, inside the timed region.
+
+  value  frames/s, whole job, inputs already resident in HBM (device-timed with CUDA events, max over ranks)
+  e2e    the same pass through the host-buffer C-ABI entry point (pinned host inputs -> H2D -> kernels -> D2H)
+  roofline       dominant kernel = rnn4's fused LSTM-layer GEMM ([rows,2560] x [2560,5120] fp32), CUDA-event timed
+  cpu_baseline   the oracle port of the reference loop on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+
+METRIC = 'frames/sec (24-joint SMPL, 60 fps streams)'
+FLOP_PER_FRAME = 2 * 60689920           # SURVEY.md §6 / BASELINE.md §3
+WEIGHT_BYTES = 243.06e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--seqs', type=int, default=1024, help='sequences per GPU')
+    ap.add_argument('--frames', type=int, default=300)
+    ap.add_argument('--conf', default='mixed')
+    ap.add_argument('--cpu-frames', type=int, default=240, help='frames of the bounded CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-stream-latency', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p['hbm_gbs'], 'tflops_burst': p['bf16_tflops'], 'tflops_sustained': p['bf16_tflops_sustained'],
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tflops_burst': 1590.0, 'tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampler running during the timed region."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out = {'sm_mhz': statistics.median(sm), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+        return out
+
+
+def build_net(seed=0):
+    from robustcap_b200 import synthetic, Net, ParametricModel
+    assets = synthetic.write_assets(synthetic.default_asset_root(), 0)
+    body = ParametricModel(assets['smpl_file'])
+    sd = synthetic.make_state_dict(seed, 'contact')     # contact/floor branches reachable (synthetic.make_state_dict)
+    net = Net(body)
+    net.load_state_dict(sd)
+    return net, sd, assets
+
+
+def make_cpu_reference(sd, assets, impl='aten'):
+    from oracle.kinematics import BodyOracle
+    from oracle.fusion import FusionOracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    return FusionOracle(sd, BodyOracle(assets['smpl_file']), lstm_impl=impl)
+
+
+def cpu_reference_pass(o, inp, frames, warm=0):
+    """One bounded sample of the reference's per-frame loop (evaluate.py:75-85) restated by the oracle."""
+    o.gravity = inp['gravity']
+    o.reset()
+    per = []
+    for t in range(frames + warm):
+        t0 = time.perf_counter()
+        kw = {'first_tran': torch.tensor([0., 0., 4.])} if t == 0 else {}
+        o.step(inp['j2dc'][0, t], inp['accc'][0, t], inp['oric'][0, t], **kw)
+        if t >= warm:
+            per.append(time.perf_counter() - t0)
+    return per
+
+
+def cpu_reference_rate(sd, assets, frames, conf, impl='aten', warm=10):
+    from robustcap_b200 import synthetic
+    o = make_cpu_reference(sd, assets, impl)
+    inp = synthetic.make_inputs(1, frames + warm, seed=99, conf=conf)
+    per = cpu_reference_pass(o, inp, frames, warm)
+    return {'value': frames / sum(per), 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '1 sequence x %d frames (after %d warm-up frames), oracle/fusion.py with torch.nn.LSTM (%s) like the '
+                      'reference, conf=%s' % (frames, warm, impl, conf),
+            'ms_per_frame_p50': 1e3 * statistics.median(per)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from robustcap_b200 import synthetic
+    assets = synthetic.write_assets(synthetic.default_asset_root(), 0)
+    sd = synthetic.make_state_dict(0, 'contact')
+    o = make_cpu_reference(sd, assets, 'aten')
+    frames = 60
+    inp = synthetic.make_inputs(1, frames, seed=99, conf=args.conf)
+    times = []
+    for i in range(max(args.warmup, 1) + args.steps):
+        t0 = time.perf_counter()
+        cpu_reference_pass(o, inp, frames)
+        if i >= max(args.warmup, 1):
+            times.append(time.perf_counter() - t0)
+    ms = 1e3 * sum(times) / len(times)
+    value = frames / (ms / 1e3)
+    line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'offline_eval %d seq x %d frames per GPU (BASELINE configs[2])' % (args.seqs, args.frames),
+                       'conf': args.conf, 'weights': 'random-init seed 0 (contact variant)'},
+            'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': 'per step: 1 sequence x %d frames of the same workload (oracle/fusion.py, torch.nn.LSTM as the '
+                                       'reference); the reference processes sequences one after another, so frames/s does not depend on '
+                                       'the number of sequences' % frames},
+            'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (there is no CPU fallback for the product path)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    from robustcap_b200 import _lib, synthetic
+    _lib.build()
+    lib = _lib.load()
+    net, sd, assets = build_net()
+    B, T = args.seqs, args.frames
+    inp = synthetic.make_inputs(B, T, seed=1000 + rank, conf=args.conf)
+    type(net).gravityc = inp['gravity'].clone()
+    j, a, o = inp['j2dc'].to(dev), inp['accc'].to(dev), inp['oric'].to(dev)
+    ft = torch.tensor([0., 0., 4.], device=dev)
+    gather_pose = gather_tran = None
+    if world > 1 and rank == 0:
+        gather_pose = [torch.empty(B, T, 24, 3, 3, device=dev) for _ in range(world)]
+        gather_tran = [torch.empty(B, T, 3, device=dev) for _ in range(world)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        pose, tran = net.forward_offline(j, a, o, first_tran=ft, use_graph=False)
+        if dist is not None:
+            dist.gather(pose, gather_pose, dst=0)
+            dist.gather(tran, gather_tran, dst=0)
+        return pose, tran
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    st = net._states[B]
+    _lib.check(lib.rc_profile_enable(st, 1))
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = lib.rc_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    launches = lib.rc_launch_count() - launches0
+    clk = clocks.stop()
+    import ctypes
+    tot_ms, nl, fpr = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    _lib.check(lib.rc_profile_collect(st, ctypes.byref(tot_ms), ctypes.byref(nl), ctypes.byref(fpr)))
+    _lib.check(lib.rc_profile_enable(st, 0))
+    t_ms = torch.tensor([ms_total], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_total = float(t_ms.item())
+    ms_step = ms_total / args.steps
+    frames_step = B * T * world
+    value = frames_step / (ms_step / 1e3)
+
+    # ---- end-to-end through the host-buffer C-ABI entry point (pinned buffers) --------------------------------
+    pin = lambda x: x.contiguous().pin_memory()
+    hj, ha, ho = pin(inp['j2dc']), pin(inp['accc']), pin(inp['oric'])
+    hp = torch.empty(B, T, 24, 3, 3).pin_memory()
+    ht = torch.empty(B, T, 3).pin_memory()
+    hft = torch.tensor([0., 0., 4.])
+    for _ in range(2):
+        net.forward_offline(hj, ha, ho, first_tran=hft, use_graph=False, out=(hp, ht))
+    barrier()
+    t0 = time.perf_counter()
+    reps = max(2, min(args.steps, 3))
+    for _ in range(reps):
+        net.forward_offline(hj, ha, ho, first_tran=hft, use_graph=False, out=(hp, ht))
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / reps
+    t_e = torch.tensor([e2e_ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t_e.item())
+    h2d = (hj.numel() + ha.numel() + ho.numel()) * 4 + 12
+    d2h = (hp.numel() + ht.numel()) * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
+    dom_flop = fpr.value * 2 * B * T * args.steps
+    dom_tflops = dom_flop / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
+    roofline = {'kernel': 'rc_gemm_kernel<LSTM> (rnn4 fused LSTM layer, fp32 SIMT)', 'bound': 'tensor',
+                'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': dom_tflops / pk['tflops_sustained'], 'peak_source': 'bf16 sustained, of ' + pk['source'],
+                'traffic': None, 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,
+                'whole_path_tflops': FLOP_PER_FRAME * B * T / (ms_step * 1e-3) / 1e12,
+                'weight_stream_gbs': WEIGHT_BYTES * T / (ms_step * 1e-3) / 1e9}
+    line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'offline_eval %d seq x %d frames per GPU (BASELINE configs[2])' % (B, T), 'conf': args.conf,
+                       'weights': 'random-init seed 0 (contact variant)', 'l2': 'inputs (%.0f MB) + weights (243 MB) per step exceed the 126 MB L2'
+                       % ((hj.numel() + ha.numel() + ho.numel()) * 4 / 1e6), 'final_gather': 'nccl gather to rank 0 inside the timed region' if world > 1 else 'none'},
+            'clocks': clk, 'gpu_launches': int(launches),
+            'e2e': {'value': frames_step / (e2e_ms / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'ms_per_step': e2e_ms},
+            'roofline': roofline}
+
+    # ---- B=1 streaming latency (BASELINE configs[1]) ---------------------------------------------------------------
+    if not args.no_stream_latency:
+        s1 = synthetic.make_inputs(1, 300, seed=5, conf='high')
+        net.reset_states()
+        lat = []
+        for t in range(300):
+            t0 = time.perf_counter()
+            net.forward_online(s1['j2dc'][0, t], s1['accc'][0, t], s1['oric'][0, t])
+            lat.append(time.perf_counter() - t0)
+        net.reset_states()
+        dj, da, do = s1['j2dc'][0].to(dev), s1['accc'][0].to(dev), s1['oric'][0].to(dev)
+        for _ in range(2):
+            net.forward_offline(dj, da, do, use_graph=True)
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        net.forward_offline(dj, da, do, use_graph=True)
+        g1.record()
+        torch.cuda.synchronize()
+        dev_us = 1e3 * g0.elapsed_time(g1) / 300
+        line['streaming'] = {'batch': 1, 'latency_p50_us_forward_online': 1e6 * statistics.median(lat[20:]),
+                             'device_us_per_frame_graph': dev_us, 'weight_stream_gbs': WEIGHT_BYTES / (dev_us * 1e-6) / 1e9,
+                             'hbm_frac': WEIGHT_BYTES / (dev_us * 1e-6) / 1e9 / pk['hbm_gbs'], 'peak_source': 'hbm copy, of ' + pk['source']}
+    if not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_reference_rate(sd, assets, args.cpu_frames, args.conf, 'aten')
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -146,6 +146,13 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* h_j2dc, const 
                              const int32_t* h_lengths, const float* h_first_tran, const int32_t* h_row_flags,
                              float* h_pose, float* h_tran, int use_graph, void* stream);
 
+/* CUDA-event timing of the dominant kernel (the fused LSTM layers of rnn4: [rows, 2H] x [2H, 4H], H = 1280) for
+ * bench.py's roofline: enable, run (non-graph launches), collect.  collect synchronises the device, returns the
+ * summed duration of the recorded launches, their number, and the algorithmic FLOPs one stream-row costs in one
+ * such launch (2 * 4H * 2H). */
+int rc_profile_enable(rc_state* s, int on);
+int rc_profile_collect(rc_state* s, double* total_ms, int64_t* launches, double* flop_per_row);
+
 /* Debug / test taps: copy a sub-net output of the last step to the host: which in {2,3,4,6,7,8}; out has
  * b * width floats (width = 69,3,69,3,144,2). */
 int rc_state_debug_output(rc_state* s, int which, float* h_out, void* stream);

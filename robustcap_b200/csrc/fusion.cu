@@ -70,6 +70,12 @@ struct rc_state {
     // cached CUDA graph of one steady-state frame
     cudaGraphExec_t graph = nullptr;
     std::vector<const void*> graph_key;
+    cudaStream_t cap_stream = nullptr;   // capture happens here (the legacy default stream cannot be captured)
+    long long graph_nodes = 0;           // kernel nodes in the captured frame (launch accounting)
+    // optional CUDA-event timing of the dominant kernel (rnn4's fused LSTM layers), see rc_profile_*
+    int prof_on = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    size_t prof_used = 0;
     // staging buffers of rc_forward_sequence_host
     float *hj = nullptr, *ha = nullptr, *ho = nullptr, *hp = nullptr, *ht = nullptr, *hft = nullptr;
     int *hlen = nullptr, *hfl = nullptr;
@@ -261,7 +267,15 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
         a.X = (l == 0) ? nb.a1 : nb.hn[0]; a.ldx = w.H; a.X2 = nb.h[l]; a.ldx2 = w.H; a.K1 = w.H; a.K2 = w.H;
         a.W = w.WL[l]; a.bias = w.bL[l]; a.N = 4 * w.H; a.Nw = 4 * w.H; a.Y = nullptr; a.ldy = 0; a.relu = 0;
         a.C = nb.c[l]; a.Hout = nb.hn[l];
+        const bool prof = s->prof_on && ni == NET4;
+        if (prof) {
+            if (s->prof_used + 2 > s->prof_ev.size()) {
+                for (int q = 0; q < 256; ++q) { cudaEvent_t e; RC_CUDA(cudaEventCreate(&e)); s->prof_ev.push_back(e); }
+            }
+            RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
+        }
         RC_TRY(launch_linear(a, B, true, stream));
+        if (prof) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     }
     {
         const long long work = (long long)B * (w.H / 4);
@@ -473,6 +487,8 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
 void rc_state_destroy(rc_state* s) {
     if (!s) return;
     if (s->graph) cudaGraphExecDestroy(s->graph);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     for (void* p : s->allocs) cudaFree(p);
     cudaFree(s->hj); cudaFree(s->ha); cudaFree(s->ho); cudaFree(s->hp); cudaFree(s->ht); cudaFree(s->hft);
     cudaFree(s->hlen); cudaFree(s->hfl);
@@ -544,9 +560,13 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
     if (!s->graph || key != s->graph_key) {
         if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
         cudaGraph_t g = nullptr;
-        RC_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const int rc = enqueue_step(s, io, 0, true, stream);
-        cudaError_t e = cudaStreamEndCapture(st, &g);
+        if (!s->cap_stream) RC_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+        RC_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const long long before = g_rc_launches.load();
+        const int rc = enqueue_step(s, io, 0, true, (void*)s->cap_stream);
+        s->graph_nodes = g_rc_launches.load() - before;
+        g_rc_launches.fetch_sub(s->graph_nodes);          // captured, not launched
+        cudaError_t e = cudaStreamEndCapture(s->cap_stream, &g);
         if (rc != RC_OK) { if (g) cudaGraphDestroy(g); return rc; }
         if (e != cudaSuccess) { rc_set_error("graph capture: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
         e = cudaGraphInstantiate(&s->graph, g, 0);
@@ -555,6 +575,7 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
         s->graph_key = key;
     }
     for (int t = 1; t < T; ++t) RC_CUDA(cudaGraphLaunch(s->graph, st));
+    g_rc_launches.fetch_add(s->graph_nodes * (long long)(T - 1));
     return RC_OK;
 }
 
@@ -594,6 +615,32 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* hj, const floa
     RC_CUDA(cudaMemcpyAsync(hp, s->hp, B * T * 216 * sizeof(float), cudaMemcpyDeviceToHost, st));
     RC_CUDA(cudaMemcpyAsync(ht, s->ht, B * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     RC_CUDA(cudaStreamSynchronize(st));
+    return RC_OK;
+}
+
+int rc_profile_enable(rc_state* s, int on) {
+    RC_ARG(s);
+    s->prof_on = on;
+    s->prof_used = 0;
+    return RC_OK;
+}
+
+int rc_profile_collect(rc_state* s, double* total_ms, int64_t* launches, double* flop_per_row) {
+    RC_ARG(s && total_ms && launches);
+    RC_CUDA(cudaDeviceSynchronize());
+    double tot = 0;
+    for (size_t i = 0; i + 1 < s->prof_used; i += 2) {
+        float ms = 0.f;
+        RC_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[i], s->prof_ev[i + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int64_t)(s->prof_used / 2);
+    if (flop_per_row) {                       // one stream-row through one rnn4 LSTM layer: 2 * 4H * 2H
+        const double H = (double)s->net->nets[NET4].H;
+        *flop_per_row = 2.0 * 4.0 * H * 2.0 * H;
+    }
+    s->prof_used = 0;
     return RC_OK;
 }
 

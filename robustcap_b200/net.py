@@ -176,7 +176,7 @@ class Net(torch.nn.Module):
 
     @torch.no_grad()
     def forward_offline(self, j2dc, accc, oric, first_tran=None, first_frame=False, lengths=None, use_graph=None,
-                        first_tran_mask=None):
+                        first_tran_mask=None, out=None):
         r"""``reset_states()`` then ``forward_online`` over every frame (evaluate.py:75-85, 93), natively batched.
 
         j2dc [T,33,3] or [B,T,33,3]; accc [..,T,6,3]; oric [..,T,6,3,3].  ``first_tran`` ([3] or [B,3]) and
@@ -209,8 +209,12 @@ class Net(torch.nn.Module):
         any_ff = int(bool((flags & 1).any()))
         use_flags = bool(flags.any())
         ln = None if lengths is None else torch.as_tensor(lengths).to('cpu', torch.int32).reshape(B).contiguous()
-        pose = torch.zeros(B, T, 24, 3, 3, **where)
-        tran = torch.zeros(B, T, 3, **where)
+        if out is not None:            # caller-provided result buffers (e.g. pinned host memory), contiguous float32
+            pose, tran = out[0].view(B, T, 24, 3, 3), out[1].view(B, T, 3)
+            assert pose.is_cuda == (not on_cpu) and pose.dtype == torch.float32
+        else:
+            pose = torch.zeros(B, T, 24, 3, 3, **where)
+            tran = torch.zeros(B, T, 3, **where)
         if on_cpu:
             _lib.check(lib.rc_forward_sequence_host(st, T, _lib.hptr(j), _lib.hptr(a), _lib.hptr(o),
                                                     _lib.hptr(ln), _lib.hptr(ft),
