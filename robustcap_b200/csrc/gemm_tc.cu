@@ -1,0 +1,314 @@
+// Fused LSTM-layer GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), fp32-accurate.
+//
+//   gates[rows, 4H] = [x | h_prev][rows, 2H] @ Wcat[4H, 2H]^T        (articulate/utils/torch/rnn.py:111 via sig_mp.py:128)
+//
+// The parity bar (1e-4 rad) rules out plain TF32/BF16/FP16 operands (weight rounding alone costs 1e-2 rad),
+// so every fp32 operand is split into two fp16 halves with an exact power-of-two rescale of the low half,
+//     x = hi + lo * 2^-11,   hi = fp16(x),   lo = fp16((x - hi) * 2^11)        (|x - hi - lo 2^-11| <= 2^-22 |x|)
+// and the product is evaluated with three kind::f16 MMAs into two fp32 TMEM accumulators
+//     main += Ahi Whi ;   corr += Ahi Wlo + Alo Whi ;   gates = main + 2^-11 corr
+// (fp16 x fp16 products are exact in the fp32 accumulator; the dropped Alo Wlo term is 2^-22 relative).  This costs 3 MMAs
+// at the fp16 rate — half the tensor time of the usual 3xTF32 scheme — and moves 4 bytes per operand element, the same as
+// fp32.  Weights are split once on the host; activation rows are gathered through the row list and split by a small
+// pre-pass (rc_split_rows_kernel), so the GEMM sees dense K-major operands that TMA can tile with the 128-byte swizzle.
+//
+// Kernel: one CTA per 128 x BN output tile, 6 warps: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
+// elected thread), warps 2-5 = epilogue (tcgen05.ld -> bias + LSTM cell update -> c (in place), h_new).  BK = 64 fp16
+// (= one 128B swizzle atom), mbarrier full/empty ring between TMA and MMA, tcgen05.commit frees stages and signals the
+// epilogue.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <vector>
+#include "rc_common.cuh"
+#include "rc_tc.cuh"
+
+namespace {
+
+constexpr int kTcBM = 128;
+constexpr int kTcBK = 64;          // fp16 elements = 128 bytes
+constexpr int kTcThreads = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (cute UMMA::SmemDescriptor:
+// start>>4 [0,14), LBO>>4 [16,30) (=1, unused for swizzled K-major), SBO>>4 [32,46) (=64), version=1 [46,48), layout
+// SWIZZLE_128B=2 [61,64)).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)64 << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
+
+struct TcArgs {
+    const float* bias;     // [4H] gate-interleaved (b_ih + b_hh)
+    float* C;              // [*, H] cell state, in place
+    float* Hout;           // [*, H] new hidden state
+    const int* rows;       // row list (stream indices); compact row i of the A operand belongs to stream rows[i]
+    const int* count;
+    int H, K;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kTcThreads, 1)
+rc_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, TcArgs a) {
+    constexpr int A_BYTES = kTcBM * kTcBK * 2;     // 16 KB
+    constexpr int W_BYTES = BN * kTcBK * 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    constexpr int TM_COLS = 2 * BN;                // main + corr accumulators
+    const int cnt = *a.count;
+    const int m0 = blockIdx.y * kTcBM;
+    if (m0 >= cnt) return;
+    const int n0 = blockIdx.x * BN;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[STAGES];
+    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = a.K / kTcBK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_expect_tx(full, STAGE_BYTES);
+                const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                tma_load_2d(base, &tmAhi, kb * kTcBK, m0, full);
+                tma_load_2d(base + A_BYTES, &tmAlo, kb * kTcBK, m0, full);
+                tma_load_2d(base + 2 * A_BYTES, &tmWhi, kb * kTcBK, n0, full);
+                tma_load_2d(base + 2 * A_BYTES + W_BYTES, &tmWlo, kb * kTcBK, n0, full);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor (cute UMMA::InstrDescriptor): c_format F32 = 1 at [4,6); a/b format F16 = 0; K-major both;
+            // n_dim = N >> 3 at [17,23); m_dim = M >> 4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+            const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint64_t dAhi = make_desc(base), dAlo = make_desc(base + A_BYTES);
+                const uint64_t dWhi = make_desc(base + 2 * A_BYTES), dWlo = make_desc(base + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+                for (int k = 0; k < kTcBK / 16; ++k) {
+                    const uint64_t adv = (uint64_t)(k * 2);      // 16 fp16 = 32 bytes = 2 x 16-byte units
+                    const uint32_t acc = (kb | k) ? 1u : 0u;
+                    tc_mma_f16(d_main, dAhi + adv, dWhi + adv, idesc, acc);
+                    tc_mma_f16(d_corr, dAhi + adv, dWlo + adv, idesc, acc);
+                    tc_mma_f16(d_corr, dAlo + adv, dWhi + adv, idesc, 1u);
+                }
+                tc_commit(smem_u32(&bar_empty[s]));              // frees the stage once these MMAs have read it
+            }
+            tc_commit(smem_u32(&bar_acc));                       // accumulators complete
+        }
+    } else {
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        mbar_wait(smem_u32(&bar_acc), 0);
+        tc_fence_after();
+        const int mrow = m0 + q * 32 + lane;
+        const int row = (mrow < cnt) ? a.rows[mrow] : -1;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t vm[32], vc[32];
+            tc_ld32(lane_base + (uint32_t)(c * 32), vm);
+            tc_ld32(lane_base + (uint32_t)(BN + c * 32), vc);
+            tc_ld_wait();
+            if (row >= 0) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int n = n0 + c * 32 + u * 4;
+                    const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
+                    const float gi = fmaf(__uint_as_float(vc[u * 4 + 0]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 0])) + b.x;
+                    const float gf = fmaf(__uint_as_float(vc[u * 4 + 1]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 1])) + b.y;
+                    const float gg = fmaf(__uint_as_float(vc[u * 4 + 2]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 2])) + b.z;
+                    const float go = fmaf(__uint_as_float(vc[u * 4 + 3]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 3])) + b.w;
+                    const size_t idx = (size_t)row * a.H + (n >> 2);
+                    const float cn = fmaf(sigm(gf), a.C[idx], sigm(gi) * tanhf(gg));
+                    a.C[idx] = cn;
+                    a.Hout[idx] = sigm(go) * tanhf(cn);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TM_COLS) : "memory");
+    }
+}
+
+// Gather the rows of a list from the two K segments, split every fp32 into (hi, lo) fp16 halves, write dense [*, K] rows.
+__global__ void __launch_bounds__(256) rc_split_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ X2, int ldx2,
+                                                             int K1, int K2, const int* __restrict__ rows, const int* __restrict__ count,
+                                                             __half* __restrict__ Ahi, __half* __restrict__ Alo) {
+    const int cnt = *count;
+    const int K = K1 + K2, q4 = K >> 2;
+    const long long total = (long long)cnt * q4;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(e / q4), k = (int)(e % q4) * 4;
+        const int r = rows[i];
+        const float4 v = (k < K1) ? *reinterpret_cast<const float4*>(X + (size_t)r * ldx + k)
+                                  : *reinterpret_cast<const float4*>(X2 + (size_t)r * ldx2 + (k - K1));
+        const float x[4] = {v.x, v.y, v.z, v.w};
+        __half hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hi[j] = __float2half_rn(x[j]);
+            lo[j] = __float2half_rn((x[j] - __half2float(hi[j])) * 2048.f);
+        }
+        __half2* ph = reinterpret_cast<__half2*>(Ahi + (size_t)i * K + k);
+        __half2* pl = reinterpret_cast<__half2*>(Alo + (size_t)i * K + k);
+        ph[0] = __halves2half2(hi[0], hi[1]); ph[1] = __halves2half2(hi[2], hi[3]);
+        pl[0] = __halves2half2(lo[0], lo[1]); pl[1] = __halves2half2(lo[2], lo[3]);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+}  // namespace
+
+int rc_tc_make_map(RcTensorMap* out, const void* base, long long rows, int K, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { rc_set_error("cuTensorMapEncodeTiled entry point not available"); return RC_ERR_CUDA; }
+    static_assert(sizeof(RcTensorMap) == sizeof(CUtensorMap), "tensor map size");
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc((CUtensorMap*)out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { rc_set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld K=%d box=%d", (int)r, rows, K, box_rows); return RC_ERR_CUDA; }
+    return RC_OK;
+}
+
+// fp32 [n] -> (hi, lo) fp16 halves on the host (weights, once at rc_net_finalize)
+void rc_tc_split_host(const float* w, size_t n, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo) {
+    hi.resize(n);
+    lo.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+        const __half h = __float2half_rn(w[i]);
+        const __half l = __float2half_rn((w[i] - __half2float(h)) * 2048.f);
+        hi[i] = *reinterpret_cast<const uint16_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint16_t*>(&l);
+    }
+}
+
+int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1, int K2, const int* rows, const int* count, int B,
+                     void* Ahi, void* Alo, void* stream) {
+    const long long work = (long long)B * ((K1 + K2) / 4);
+    const int grid = (int)std::min<long long>(rc_cdiv(work, 256), 148 * 8);
+    RC_LAUNCH(rc_split_rows_kernel, grid, 256, 0, stream, X, ldx, X2, ldx2, K1, K2, rows, count, (__half*)Ahi, (__half*)Alo);
+    RC_CHECK_LAUNCH();
+    return RC_OK;
+}
+
+int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream) {
+    constexpr int BN = RC_TC_BN, STAGES = 2;
+    constexpr int SMEM = STAGES * (2 * kTcBM * kTcBK * 2 + 2 * BN * kTcBK * 2) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RC_CUDA(cudaFuncSetAttribute(rc_lstm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    TcArgs a;
+    a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
+    dim3 grid(4 * H / BN, rc_cdiv(B, kTcBM));
+    RC_LAUNCH((rc_lstm_tc_kernel<BN, STAGES>), grid, kTcThreads, SMEM, stream, *(const CUtensorMap*)mAhi, *(const CUtensorMap*)mAlo,
+              *(const CUtensorMap*)mWhi, *(const CUtensorMap*)mWlo, a);
+    RC_CHECK_LAUNCH();
+    return RC_OK;
+}
