@@ -117,10 +117,25 @@ def build_net(seed=0):
 
 
 def make_cpu_reference(sd, assets, impl='aten'):
+    """Oracle port of the reference loop with the thread count that maximises its throughput on this host: the work is
+    GEMV-sized, and torch's default of one thread per core (128 on the B200 box) is far slower than a few threads."""
+    from robustcap_b200 import synthetic
     from oracle.kinematics import BodyOracle
     from oracle.fusion import FusionOracle
-    torch.set_num_threads(os.cpu_count() or 1)
-    return FusionOracle(sd, BodyOracle(assets['smpl_file']), lstm_impl=impl)
+    o = FusionOracle(sd, BodyOracle(assets['smpl_file']), lstm_impl=impl)
+    ncpu = os.cpu_count() or 1
+    inp = synthetic.make_inputs(1, 6, seed=98, conf='mixed')
+    best, best_t = None, None
+    for n in sorted({1, 2, 4, 8, 16, 32, ncpu}):
+        if n > ncpu:
+            continue
+        torch.set_num_threads(n)
+        per = cpu_reference_pass(o, inp, 4, warm=2)
+        t = statistics.median(per)
+        if best_t is None or t < best_t:
+            best, best_t = n, t
+    torch.set_num_threads(best)
+    return o
 
 
 def cpu_reference_pass(o, inp, frames, warm=0):
@@ -282,7 +297,8 @@ def main():
     # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
     dom_flop = fpr.value * 2 * B * T * args.steps
     dom_tflops = dom_flop / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
-    roofline = {'kernel': 'rc_gemm_kernel<LSTM> (rnn4 fused LSTM layer, fp32 SIMT)', 'bound': 'tensor',
+    roofline = {'kernel': 'rc_lstm_tc_kernel (rnn4 fused LSTM layer [rows,2560]x[2560,5120]; tcgen05 kind::f16 on split-fp16 operands, '
+                          '3 MMAs per fp32-accurate product; the event pair also covers the row-gather/split pre-pass)', 'bound': 'tensor',
                 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': dom_tflops / pk['tflops_sustained'], 'peak_source': 'bf16 sustained, of ' + pk['source'],
                 'traffic': None, 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,

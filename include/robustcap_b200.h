@@ -111,6 +111,9 @@ int rc_net_set_config(rc_net* n, const rc_net_config* cfg);
 int rc_net_set_tensor(rc_net* n, const char* key, const float* h_data, int64_t numel);
 int rc_net_finalize(rc_net* n);
 int64_t rc_net_weight_bytes(const rc_net* n);     /* bytes of packed per-frame weights resident in HBM */
+/* Batched (B > 8) LSTM-layer GEMM back end: 1 (default) = tcgen05 tensor cores on split-fp16 operands with fp32-level
+ * accuracy (gemm_tc.cu), 0 = fp32 SIMT tiles.  B <= 8 always uses the weight-streaming GEMV kernels. */
+int rc_net_set_gemm_mode(rc_net* n, int mode);
 
 int rc_state_create(rc_state** out, const rc_net* net, int32_t b);
 void rc_state_destroy(rc_state* s);

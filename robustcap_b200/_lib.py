@@ -89,6 +89,7 @@ _SIGS = {
     'rc_net_set_tensor': (i32, [vp, ctypes.c_char_p, vp, i64]),
     'rc_net_finalize': (i32, [vp]),
     'rc_net_weight_bytes': (i64, [vp]),
+    'rc_net_set_gemm_mode': (i32, [vp, i32]),
     'rc_state_create': (i32, [ctypes.POINTER(vp), vp, i32]),
     'rc_state_destroy': (None, [vp]),
     'rc_state_reset': (i32, [vp, vp]),
@@ -105,7 +106,6 @@ _OPTIONAL_SIGS = {
     'rc_smplify_create': (i32, [ctypes.POINTER(vp), vp, vp, vp, vp, i32]),
     'rc_smplify_destroy': (None, [vp]),
     'rc_smplify_loss_grad': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
-    'rc_net_set_gemm_mode': (i32, [vp, i32]),
 }
 
 

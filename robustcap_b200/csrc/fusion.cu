@@ -18,6 +18,7 @@
 #include "rc_model.cuh"
 #include "rc_linear.cuh"
 #include "rc_pack.h"
+#include "rc_tc.cuh"
 
 namespace {
 
@@ -35,6 +36,8 @@ enum { L_ALL = 0, L_HI, L_6A, L_6B, L_LATE, L_INIT, NLISTS };
 struct NetDev {
     int in = 0, K1 = 0, H = 0, out = 0, out4 = 0;
     float *W1 = nullptr, *b1 = nullptr, *WL[2] = {nullptr, nullptr}, *bL[2] = {nullptr, nullptr}, *W2 = nullptr, *b2 = nullptr;
+    uint16_t *WLhi[2] = {nullptr, nullptr}, *WLlo[2] = {nullptr, nullptr};   // split-fp16 copies for the tensor-core path
+    RcTensorMap mWhi[2], mWlo[2];
 };
 struct NetBuf {
     float *h[2] = {nullptr, nullptr}, *c[2] = {nullptr, nullptr}, *hn[2] = {nullptr, nullptr}, *a1 = nullptr;
@@ -51,6 +54,8 @@ struct rc_net {
     float *Wi[3] = {nullptr, nullptr, nullptr}, *bi[3] = {nullptr, nullptr, nullptr};   // init_net
     int64_t weight_bytes = 0;
     std::vector<void*> allocs;
+    int gemm_mode = 1;          // 0 = fp32 SIMT tiles, 1 = tcgen05 split-fp16 (batches > 8 streams)
+    bool tc_ready = false;
 };
 
 struct rc_state {
@@ -62,6 +67,9 @@ struct rc_state {
     float *Y3 = nullptr, *Y6 = nullptr, *Y7 = nullptr, *Y8 = nullptr, *Ydump = nullptr;
     float *I1 = nullptr, *I2 = nullptr, *I3 = nullptr;
     float *rcr = nullptr, *conf = nullptr, *lerpw = nullptr, *gravity = nullptr;
+    uint16_t *Ahi = nullptr, *Alo = nullptr;     // [Bpad, 2*Hmax] split activations (tensor-core path)
+    RcTensorMap mAhi[NNETS], mAlo[NNETS];
+    bool tc_ready = false;
     int* flags = nullptr;
     int* lists = nullptr;      // [NLISTS][B]
     int* counts = nullptr;     // [NLISTS]
@@ -274,7 +282,12 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
             }
             RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
         }
-        RC_TRY(launch_linear(a, B, true, stream));
+        if (s->net->gemm_mode == 1 && s->tc_ready && B > 8) {
+            RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, rows, count, B, s->Ahi, s->Alo, stream));
+            RC_TRY(rc_tc_lstm_layer(&s->mAhi[ni], &s->mAlo[ni], &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
+        } else {
+            RC_TRY(launch_linear(a, B, true, stream));
+        }
         if (prof) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     }
     {
@@ -360,7 +373,7 @@ int pack_linear(rc_net* n, const std::string& prefix, int out, int in, int out_p
     return RC_OK;
 }
 
-int pack_lstm(rc_net* n, const std::string& prefix, int layer, int H, float** dW, float** db) {
+int pack_lstm(rc_net* n, const std::string& prefix, int layer, int H, float** dW, float** db, uint16_t** dWhi, uint16_t** dWlo) {
     const std::string sfx = "_l" + std::to_string(layer);
     const std::vector<float>* wih = get_staged(n, prefix + ".rnn.weight_ih" + sfx, (size_t)4 * H * H);
     const std::vector<float>* whh = get_staged(n, prefix + ".rnn.weight_hh" + sfx, (size_t)4 * H * H);
@@ -372,6 +385,14 @@ int pack_lstm(rc_net* n, const std::string& prefix, int layer, int H, float** dW
     RC_TRY(upload(n->allocs, dW, pw));
     RC_TRY(upload(n->allocs, db, pb));
     n->weight_bytes += (int64_t)(pw.size() + pb.size()) * 4;
+    if (dWhi) {
+        std::vector<uint16_t> hi, lo;
+        rc_tc_split_host(pw.data(), pw.size(), hi, lo);
+        RC_TRY(dev_alloc(n->allocs, dWhi, hi.size()));
+        RC_TRY(dev_alloc(n->allocs, dWlo, lo.size()));
+        RC_CUDA(cudaMemcpy(*dWhi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+        RC_CUDA(cudaMemcpy(*dWlo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    }
     return RC_OK;
 }
 
@@ -436,7 +457,12 @@ int rc_net_finalize(rc_net* n) {
         d.in = kNetIn[i]; d.K1 = kNetK1[i]; d.H = kNetH[i]; d.out = kNetOut[i]; d.out4 = (d.out + 3) / 4 * 4;
         const std::string p = "rnn" + std::to_string(kNetId[i]);
         RC_TRY(pack_linear(n, p + ".linear1", d.H, d.in, d.H, d.K1, &d.W1, &d.b1));
-        for (int l = 0; l < 2; ++l) RC_TRY(pack_lstm(n, p, l, d.H, &d.WL[l], &d.bL[l]));
+        for (int l = 0; l < 2; ++l) RC_TRY(pack_lstm(n, p, l, d.H, &d.WL[l], &d.bL[l], &d.WLhi[l], &d.WLlo[l]));
+        n->tc_ready = true;
+        for (int l = 0; l < 2 && n->tc_ready; ++l) {
+            if (rc_tc_make_map(&d.mWhi[l], d.WLhi[l], 4LL * d.H, 2 * d.H, RC_TC_BN) != RC_OK ||
+                rc_tc_make_map(&d.mWlo[l], d.WLlo[l], 4LL * d.H, 2 * d.H, RC_TC_BN) != RC_OK) n->tc_ready = false;
+        }
         RC_TRY(pack_linear(n, p + ".linear2", d.out, d.H, d.out4, d.H, &d.W2, &d.b2));
     }
     const int64_t per_frame = n->weight_bytes;
@@ -450,6 +476,13 @@ int rc_net_finalize(rc_net* n) {
 }
 
 int64_t rc_net_weight_bytes(const rc_net* n) { return n ? n->weight_bytes : 0; }
+
+int rc_net_set_gemm_mode(rc_net* n, int mode) {
+    RC_ARG(n && (mode == 0 || mode == 1));
+    if (mode == 1 && !n->tc_ready) { rc_set_error("tensor-core path unavailable (tensor maps could not be created)"); return RC_ERR_STATE; }
+    n->gemm_mode = mode;
+    return RC_OK;
+}
 
 int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
     RC_ARG(out && net && B > 0);
@@ -468,6 +501,22 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
     A(&s->Y3, (size_t)B * 4); A(&s->Y6, (size_t)B * 4); A(&s->Y7, (size_t)B * 144); A(&s->Y8, (size_t)B * 4);
     A(&s->I1, (size_t)B * 512); A(&s->I2, (size_t)B * 1024); A(&s->I3, (size_t)B * 2048);
     A(&s->rcr, (size_t)B * 9); A(&s->conf, (size_t)B); A(&s->lerpw, (size_t)B * 2); A(&s->gravity, 4);
+    if (rc == RC_OK && net->tc_ready && B > 8) {
+        const long long Bpad = (long long)((B + 127) / 128) * 128;
+        int Hmax = 0;
+        for (int i = 0; i < NNETS; ++i) Hmax = std::max(Hmax, net->nets[i].H);
+        rc = dev_alloc(s->allocs, &s->Ahi, (size_t)Bpad * 2 * Hmax);
+        if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->Alo, (size_t)Bpad * 2 * Hmax);
+        if (rc == RC_OK) {
+            cudaMemset(s->Ahi, 0, (size_t)Bpad * 2 * Hmax * 2);
+            cudaMemset(s->Alo, 0, (size_t)Bpad * 2 * Hmax * 2);
+            s->tc_ready = true;
+            for (int i = 0; i < NNETS && s->tc_ready; ++i) {
+                if (rc_tc_make_map(&s->mAhi[i], s->Ahi, Bpad, 2 * net->nets[i].H, 128) != RC_OK ||
+                    rc_tc_make_map(&s->mAlo[i], s->Alo, Bpad, 2 * net->nets[i].H, 128) != RC_OK) s->tc_ready = false;
+            }
+        }
+    }
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->flags, (size_t)B);
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->lists, (size_t)NLISTS * B);
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->counts, (size_t)NLISTS);

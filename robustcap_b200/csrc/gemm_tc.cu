@@ -18,6 +18,8 @@
 // epilogue.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
+#include <algorithm>
 #include <vector>
 #include "rc_common.cuh"
 #include "rc_tc.cuh"
@@ -36,16 +38,23 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}\n" ::"r"(bar), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a mis-programmed TMA / MMA must trap instead of hanging the GPU (about 2 s at 2 GHz).
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -295,20 +304,31 @@ int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1,
     return RC_OK;
 }
 
-int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
-                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream) {
-    constexpr int BN = RC_TC_BN, STAGES = 2;
+template <int BN, int STAGES>
+int launch_tc(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo, const TcArgs& a,
+              int B, void* stream) {
     constexpr int SMEM = STAGES * (2 * kTcBM * kTcBK * 2 + 2 * BN * kTcBK * 2) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
         RC_CUDA(cudaFuncSetAttribute(rc_lstm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
-    TcArgs a;
-    a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
-    dim3 grid(4 * H / BN, rc_cdiv(B, kTcBM));
+    dim3 grid(4 * a.H / BN, rc_cdiv(B, kTcBM));
     RC_LAUNCH((rc_lstm_tc_kernel<BN, STAGES>), grid, kTcThreads, SMEM, stream, *(const CUtensorMap*)mAhi, *(const CUtensorMap*)mAlo,
               *(const CUtensorMap*)mWhi, *(const CUtensorMap*)mWlo, a);
     RC_CHECK_LAUNCH();
     return RC_OK;
+}
+
+int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream) {
+    TcArgs a;
+    a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
+    static int stages = 0;
+    if (!stages) {
+        const char* e = getenv("RC_TC_STAGES");       // tuning knob (2 or 3 ring stages of 64 KB)
+        stages = (e && atoi(e) == 2) ? 2 : 3;
+    }
+    if (stages == 2) return launch_tc<RC_TC_BN, 2>(mAhi, mAlo, mWhi, mWlo, a, B, stream);
+    return launch_tc<RC_TC_BN, 3>(mAhi, mAlo, mWhi, mWlo, a, B, stream);
 }

@@ -1,0 +1,20 @@
+// Interface of the tensor-core (tcgen05) LSTM-layer GEMM (gemm_tc.cu) used by fusion.cu.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <vector>
+
+#define RC_TC_BN 128                  // output-tile width (gate columns) = 32 hidden units
+
+struct alignas(64) RcTensorMap { unsigned char opaque[128]; };   // == CUtensorMap
+
+// 2-D fp16 [rows, K] row-major tensor map, box = 64 (K) x box_rows, 128-byte swizzle
+int rc_tc_make_map(RcTensorMap* out, const void* base, long long rows, int K, int box_rows);
+// fp32 -> (hi, lo) fp16 halves with lo pre-scaled by 2^11
+void rc_tc_split_host(const float* w, size_t n, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
+// gather list rows from [X | X2], split to fp16 halves, write dense [*, K1+K2]
+int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1, int K2, const int* rows, const int* count, int B,
+                     void* Ahi, void* Alo, void* stream);
+// fused LSTM layer on the tensor cores over the rows of a list
+int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream);

@@ -135,6 +135,12 @@ class Net(torch.nn.Module):
         self._dirty = True
         return out
 
+    def set_gemm_mode(self, mode):
+        """Batched (B > 8) LSTM GEMM back end: 1 = tcgen05 tensor cores on split-fp16 operands (default), 0 = fp32 SIMT."""
+        self._ensure_native()
+        _lib.check(_lib.load().rc_net_set_gemm_mode(self._net, int(mode)))
+        self._gemm_mode = int(mode)
+
     def weight_bytes(self):
         self._ensure_native()
         return int(_lib.load().rc_net_weight_bytes(self._net))

@@ -152,8 +152,9 @@ def test_forward_online_golden(rb, body, golden_dir, case):
     assert terr < POS_TOL, terr
 
 
+@pytest.mark.parametrize('gemm_mode', [1, 0], ids=['tcgen05', 'simt'])
 @pytest.mark.parametrize('variant', ['default', 'contact'])
-def test_forward_offline_batched_golden(rb, body, golden_dir, variant):
+def test_forward_offline_batched_golden(rb, body, golden_dir, variant, gemm_mode):
     """Batched forward_offline (tiled GEMM kernels, B > 8), ragged lengths, per-row start modes, vs the reference."""
     cases = [c for c in ONLINE_CASES if c[2] == variant]
     cases = cases * (12 // len(cases) + 1)
@@ -169,6 +170,7 @@ def test_forward_offline_batched_golden(rb, body, golden_dir, variant):
     ff = torch.tensor([c[5] == 'first_frame' for c in cases])
     ftm = torch.tensor([c[5] == 'first_tran' for c in cases])
     net = get_net(rb, body, 0, variant)
+    net.set_gemm_mode(gemm_mode)
     rb.Net.gravityc = gs[0]['gravity'].clone()
     for use_graph in (False, True):
         pose, tran = net.forward_offline(j.cuda(), a.cuda(), o.cuda(), first_tran=torch.tensor([0., 0., 4.]), first_frame=ff,
@@ -185,6 +187,30 @@ def test_forward_offline_batched_golden(rb, body, golden_dir, variant):
     p2, t2 = net.forward_offline(j, a, o, first_tran=torch.tensor([0., 0., 4.]), first_frame=ff, lengths=lengths, first_tran_mask=ftm)
     assert p2.device.type == 'cpu'
     assert torch.equal(p2, pose) and torch.equal(t2, tran)
+    net.set_gemm_mode(1)
+
+
+def test_tensor_core_gemm_matches_simt(rb, body):
+    """The split-fp16 tcgen05 LSTM GEMM against the fp32 SIMT GEMM on the same batch: 200 sequences (ragged M tile),
+    10 frames.  Both are fp32-accurate evaluations of the same dot products, so they agree to reduction-order noise."""
+    net = get_net(rb, body, 0, 'contact')
+    inp = synthetic.make_inputs(200, 10, seed=31, conf='mixed')
+    rb.Net.gravityc = inp['gravity'].clone()
+    j, a, o = inp['j2dc'].cuda(), inp['accc'].cuda(), inp['oric'].cuda()
+    ft = torch.tensor([0., 0., 4.])
+    net.set_gemm_mode(0)
+    p0, t0 = net.forward_offline(j, a, o, first_tran=ft)
+    d0 = {k: v.clone() for k, v in net.debug_outputs(200).items()}
+    net.set_gemm_mode(1)
+    p1, t1 = net.forward_offline(j, a, o, first_tran=ft)
+    d1 = net.debug_outputs(200)
+    for k in d0:
+        err = (d0[k] - d1[k]).abs().max().item()
+        print('sub-net %d: max |simt - tc| = %.2e (scale %.2e)' % (k, err, d0[k].abs().max().item()))
+    ang = pose_angle(p0.cpu(), p1.cpu()).max().item()
+    terr = (t0 - t1).abs().max().item()
+    print('pose %.2e rad, tran %.2e m' % (ang, terr))
+    assert ang < 5e-5 and terr < 1e-4
 
 
 def test_offline_vs_oracle_seeded(rb, body, assets):
