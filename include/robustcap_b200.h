@@ -149,6 +149,11 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* h_j2dc, const 
                              const int32_t* h_lengths, const float* h_first_tran, const int32_t* h_row_flags,
                              float* h_pose, float* h_tran, int use_graph, void* stream);
 
+/* Test tap: one fused LSTM layer of sub-net `ni` (0..5 = rnn2,3,4,6,7,8), layer 0/1, on caller-provided device data for
+ * all b rows of the state: d_x [b,H], d_hprev [b,H], d_c [b,H] (in place), d_hout [b,H]; mode as rc_net_set_gemm_mode. */
+int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* d_x, const float* d_hprev, float* d_c,
+                        float* d_hout, void* stream);
+
 /* CUDA-event timing of the dominant kernel (the fused LSTM layers of rnn4: [rows, 2H] x [2H, 4H], H = 1280) for
  * bench.py's roofline: enable, run (non-graph launches), collect.  collect synchronises the device, returns the
  * summed duration of the recorded launches, their number, and the algorithmic FLOPs one stream-row costs in one

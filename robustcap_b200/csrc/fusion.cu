@@ -38,6 +38,9 @@ struct NetDev {
     float *W1 = nullptr, *b1 = nullptr, *WL[2] = {nullptr, nullptr}, *bL[2] = {nullptr, nullptr}, *W2 = nullptr, *b2 = nullptr;
     uint16_t *WLhi[2] = {nullptr, nullptr}, *WLlo[2] = {nullptr, nullptr};   // split-fp16 copies for the tensor-core path
     RcTensorMap mWhi[2], mWlo[2];
+    int K1p = 0, outp = 0;                                                   // linear1 K padded to 64, linear2 rows padded to RC_TC_BN
+    uint16_t *W1hi = nullptr, *W1lo = nullptr, *W2hi = nullptr, *W2lo = nullptr;
+    RcTensorMap mW1hi, mW1lo, mW2hi, mW2lo;
 };
 struct NetBuf {
     float *h[2] = {nullptr, nullptr}, *c[2] = {nullptr, nullptr}, *hn[2] = {nullptr, nullptr}, *a1 = nullptr;
@@ -68,7 +71,9 @@ struct rc_state {
     float *I1 = nullptr, *I2 = nullptr, *I3 = nullptr;
     float *rcr = nullptr, *conf = nullptr, *lerpw = nullptr, *gravity = nullptr;
     uint16_t *Ahi = nullptr, *Alo = nullptr;     // [Bpad, 2*Hmax] split activations (tensor-core path)
-    RcTensorMap mAhi[NNETS], mAlo[NNETS];
+    RcTensorMap mAhi[NNETS], mAlo[NNETS];          // A operand as [Bpad, 2H]  (LSTM layers)
+    RcTensorMap mA1hi[NNETS], mA1lo[NNETS];        //              [Bpad, K1p] (linear1)
+    RcTensorMap mA2hi[NNETS], mA2lo[NNETS];        //              [Bpad, H]   (linear2)
     bool tc_ready = false;
     int* flags = nullptr;
     int* lists = nullptr;      // [NLISTS][B]
@@ -269,7 +274,13 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
     // linear1 + relu
     a.X = X; a.ldx = w.K1; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.K1; a.K2 = 0;
     a.W = w.W1; a.bias = w.b1; a.N = w.H; a.Nw = w.H; a.Y = nb.a1; a.ldy = w.H; a.relu = 1; a.H = w.H;
-    RC_TRY(launch_linear(a, B, false, stream));
+    const bool tc = s->net->gemm_mode == 1 && s->tc_ready && B > 8;
+    if (tc) {
+        RC_TRY(rc_tc_split_rows(X, w.K1, nullptr, 0, w.K1, 0, w.K1p, rows, count, B, s->Ahi, s->Alo, stream));
+        RC_TRY(rc_tc_linear(&s->mA1hi[ni], &s->mA1lo[ni], &w.mW1hi, &w.mW1lo, w.b1, nb.a1, w.H, w.H, w.K1p, 1, rows, count, B, stream));
+    } else {
+        RC_TRY(launch_linear(a, B, false, stream));
+    }
     // LSTM layers
     for (int l = 0; l < 2; ++l) {
         a.X = (l == 0) ? nb.a1 : nb.hn[0]; a.ldx = w.H; a.X2 = nb.h[l]; a.ldx2 = w.H; a.K1 = w.H; a.K2 = w.H;
@@ -282,8 +293,8 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
             }
             RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
         }
-        if (s->net->gemm_mode == 1 && s->tc_ready && B > 8) {
-            RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, rows, count, B, s->Ahi, s->Alo, stream));
+        if (tc) {
+            RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi, s->Alo, stream));
             RC_TRY(rc_tc_lstm_layer(&s->mAhi[ni], &s->mAlo[ni], &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
         } else {
             RC_TRY(launch_linear(a, B, true, stream));
@@ -299,7 +310,12 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
     if (Y) {
         a.X = nb.hn[1]; a.ldx = w.H; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.H; a.K2 = 0;
         a.W = w.W2; a.bias = w.b2; a.N = w.out; a.Nw = w.out4; a.Y = Y; a.ldy = ldy; a.relu = 0; a.C = nullptr; a.Hout = nullptr;
-        RC_TRY(launch_linear(a, B, false, stream));
+        if (tc) {
+            RC_TRY(rc_tc_split_rows(nb.hn[1], w.H, nullptr, 0, w.H, 0, w.H, rows, count, B, s->Ahi, s->Alo, stream));
+            RC_TRY(rc_tc_linear(&s->mA2hi[ni], &s->mA2lo[ni], &w.mW2hi, &w.mW2lo, w.b2, Y, ldy, w.out, w.H, 0, rows, count, B, stream));
+        } else {
+            RC_TRY(launch_linear(a, B, false, stream));
+        }
     }
     return RC_OK;
 }
@@ -361,7 +377,8 @@ const std::vector<float>* get_staged(rc_net* n, const std::string& key, size_t n
     return &it->second;
 }
 
-int pack_linear(rc_net* n, const std::string& prefix, int out, int in, int out_pad, int in_pad, float** dW, float** db) {
+int pack_linear(rc_net* n, const std::string& prefix, int out, int in, int out_pad, int in_pad, float** dW, float** db,
+                int tc_out_pad = 0, int tc_in_pad = 0, uint16_t** dWhi = nullptr, uint16_t** dWlo = nullptr) {
     const std::vector<float>* w = get_staged(n, prefix + ".weight", (size_t)out * in);
     const std::vector<float>* b = get_staged(n, prefix + ".bias", (size_t)out);
     if (!w || !b) return RC_ERR_STATE;
@@ -370,6 +387,16 @@ int pack_linear(rc_net* n, const std::string& prefix, int out, int in, int out_p
     RC_TRY(upload(n->allocs, dW, pw));
     RC_TRY(upload(n->allocs, db, pb));
     n->weight_bytes += (int64_t)(pw.size() + pb.size()) * 4;
+    if (dWhi) {                                   // tensor-core copy: rows padded to the tile width, K to 64, split fp16
+        std::vector<float> tw, tb;
+        std::vector<uint16_t> hi, lo;
+        rc_pack_linear(w->data(), b->data(), out, in, tc_out_pad, tc_in_pad, tw, tb);
+        rc_tc_split_host(tw.data(), tw.size(), hi, lo);
+        RC_TRY(dev_alloc(n->allocs, dWhi, hi.size()));
+        RC_TRY(dev_alloc(n->allocs, dWlo, lo.size()));
+        RC_CUDA(cudaMemcpy(*dWhi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+        RC_CUDA(cudaMemcpy(*dWlo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+    }
     return RC_OK;
 }
 
@@ -456,14 +483,21 @@ int rc_net_finalize(rc_net* n) {
         NetDev& d = n->nets[i];
         d.in = kNetIn[i]; d.K1 = kNetK1[i]; d.H = kNetH[i]; d.out = kNetOut[i]; d.out4 = (d.out + 3) / 4 * 4;
         const std::string p = "rnn" + std::to_string(kNetId[i]);
-        RC_TRY(pack_linear(n, p + ".linear1", d.H, d.in, d.H, d.K1, &d.W1, &d.b1));
+        d.K1p = (d.K1 + 63) / 64 * 64;
+        d.outp = (d.out + RC_TC_BN - 1) / RC_TC_BN * RC_TC_BN;
+        RC_TRY(pack_linear(n, p + ".linear1", d.H, d.in, d.H, d.K1, &d.W1, &d.b1, d.H, d.K1p, &d.W1hi, &d.W1lo));
         for (int l = 0; l < 2; ++l) RC_TRY(pack_lstm(n, p, l, d.H, &d.WL[l], &d.bL[l], &d.WLhi[l], &d.WLlo[l]));
         n->tc_ready = true;
         for (int l = 0; l < 2 && n->tc_ready; ++l) {
             if (rc_tc_make_map(&d.mWhi[l], d.WLhi[l], 4LL * d.H, 2 * d.H, RC_TC_BN) != RC_OK ||
                 rc_tc_make_map(&d.mWlo[l], d.WLlo[l], 4LL * d.H, 2 * d.H, RC_TC_BN) != RC_OK) n->tc_ready = false;
         }
-        RC_TRY(pack_linear(n, p + ".linear2", d.out, d.H, d.out4, d.H, &d.W2, &d.b2));
+        RC_TRY(pack_linear(n, p + ".linear2", d.out, d.H, d.out4, d.H, &d.W2, &d.b2, d.outp, d.H, &d.W2hi, &d.W2lo));
+        if (n->tc_ready) {
+            if (rc_tc_make_map(&d.mW1hi, d.W1hi, d.H, d.K1p, RC_TC_BN) != RC_OK || rc_tc_make_map(&d.mW1lo, d.W1lo, d.H, d.K1p, RC_TC_BN) != RC_OK ||
+                rc_tc_make_map(&d.mW2hi, d.W2hi, d.outp, d.H, RC_TC_BN) != RC_OK || rc_tc_make_map(&d.mW2lo, d.W2lo, d.outp, d.H, RC_TC_BN) != RC_OK)
+                n->tc_ready = false;
+        }
     }
     const int64_t per_frame = n->weight_bytes;
     const int kin[3] = {kInitK0, 512, 1024};
@@ -512,8 +546,11 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
             cudaMemset(s->Alo, 0, (size_t)Bpad * 2 * Hmax * 2);
             s->tc_ready = true;
             for (int i = 0; i < NNETS && s->tc_ready; ++i) {
-                if (rc_tc_make_map(&s->mAhi[i], s->Ahi, Bpad, 2 * net->nets[i].H, 128) != RC_OK ||
-                    rc_tc_make_map(&s->mAlo[i], s->Alo, Bpad, 2 * net->nets[i].H, 128) != RC_OK) s->tc_ready = false;
+                const NetDev& d = net->nets[i];
+                if (rc_tc_make_map(&s->mAhi[i], s->Ahi, Bpad, 2 * d.H, 128) != RC_OK || rc_tc_make_map(&s->mAlo[i], s->Alo, Bpad, 2 * d.H, 128) != RC_OK ||
+                    rc_tc_make_map(&s->mA1hi[i], s->Ahi, Bpad, d.K1p, 128) != RC_OK || rc_tc_make_map(&s->mA1lo[i], s->Alo, Bpad, d.K1p, 128) != RC_OK ||
+                    rc_tc_make_map(&s->mA2hi[i], s->Ahi, Bpad, d.H, 128) != RC_OK || rc_tc_make_map(&s->mA2lo[i], s->Alo, Bpad, d.H, 128) != RC_OK)
+                    s->tc_ready = false;
             }
         }
     }
@@ -664,6 +701,34 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* hj, const floa
     RC_CUDA(cudaMemcpyAsync(hp, s->hp, B * T * 216 * sizeof(float), cudaMemcpyDeviceToHost, st));
     RC_CUDA(cudaMemcpyAsync(ht, s->ht, B * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     RC_CUDA(cudaStreamSynchronize(st));
+    return RC_OK;
+}
+
+// Test tap: run ONE fused LSTM layer (sub-net ni in 0..5 = rnn2,3,4,6,7,8; layer 0/1) on caller data for all B rows of the
+// state: x [B,H], h_prev [B,H], c [B,H] (updated in place), h_out [B,H]; mode 0 = fp32 SIMT/GEMV, 1 = tcgen05.
+int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* x, const float* hprev, float* c, float* hout, void* stream) {
+    RC_ARG(s && ni >= 0 && ni < NNETS && (layer == 0 || layer == 1) && x && hprev && c && hout);
+    const NetDev& w = s->net->nets[ni];
+    const int B = s->B;
+    std::vector<int> ident(B);
+    for (int i = 0; i < B; ++i) ident[i] = i;
+    RC_CUDA(cudaMemcpyAsync(s->lists + (size_t)L_ALL * B, ident.data(), (size_t)B * sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    RC_CUDA(cudaMemcpyAsync(s->counts + L_ALL, &B, sizeof(int), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    RC_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const int* rows = s->lists + (size_t)L_ALL * B;
+    const int* count = s->counts + L_ALL;
+    if (mode == 1) {
+        if (!(s->tc_ready && B > 8)) { rc_set_error("tensor-core path not available for this state"); return RC_ERR_STATE; }
+        RC_TRY(rc_tc_split_rows(x, w.H, hprev, w.H, w.H, w.H, 2 * w.H, rows, count, B, s->Ahi, s->Alo, stream));
+        RC_TRY(rc_tc_lstm_layer(&s->mAhi[ni], &s->mAlo[ni], &w.mWhi[layer], &w.mWlo[layer], w.bL[layer], c, hout, w.H, rows, count, B, stream));
+    } else {
+        RcLinear a;
+        memset(&a, 0, sizeof(a));
+        a.rows = rows; a.count = count;
+        a.X = x; a.ldx = w.H; a.X2 = hprev; a.ldx2 = w.H; a.K1 = w.H; a.K2 = w.H;
+        a.W = w.WL[layer]; a.bias = w.bL[layer]; a.N = 4 * w.H; a.Nw = 4 * w.H; a.C = c; a.Hout = hout; a.H = w.H;
+        RC_TRY(launch_linear(a, B, true, stream));
+    }
     return RC_OK;
 }
 

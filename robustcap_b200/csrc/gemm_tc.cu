@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 #include <vector>
 #include "rc_common.cuh"
@@ -101,22 +102,29 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 __device__ __forceinline__ float sigm(float x) { return 1.f / (1.f + expf(-x)); }
 
 struct TcArgs {
-    const float* bias;     // [4H] gate-interleaved (b_ih + b_hh)
-    float* C;              // [*, H] cell state, in place
-    float* Hout;           // [*, H] new hidden state
+    const float* bias;     // LSTM: [4H] gate-interleaved (b_ih + b_hh); linear: [N]
+    float* C;              // LSTM: [*, H] cell state, in place
+    float* Hout;           // LSTM: [*, H] new hidden state
+    float* Y; int ldy;     // linear: output rows
+    int N, relu;           // linear: valid outputs, activation
     const int* rows;       // row list (stream indices); compact row i of the A operand belongs to stream rows[i]
     const int* count;
     int H, K;
 };
 
-template <int BN, int STAGES>
+// TMEM plan (512 columns): three "main" accumulators used round-robin over the K steps + one "corr" accumulator.
+// The tensor core adds into the fp32 accumulator with truncation, a drift that grows with the number of MMAs chained on
+// one accumulator (measured: 3.6x the rms error of sequential fp32 FMAs at K = 2560); three independent chains cut it 3x
+// and are summed in the epilogue with round-to-nearest adds.  corr holds values 2^11 times smaller, its drift is moot.
+template <int BN, int STAGES, bool LSTM>
 __global__ void __launch_bounds__(kTcThreads, 1)
-rc_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-                  const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, TcArgs a) {
+rc_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+             const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, TcArgs a) {
     constexpr int A_BYTES = kTcBM * kTcBK * 2;     // 16 KB
     constexpr int W_BYTES = BN * kTcBK * 2;
     constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-    constexpr int TM_COLS = 2 * BN;                // main + corr accumulators
+    constexpr int TM_COLS = 4 * BN;                // 3 x main + corr
+    static_assert(TM_COLS == 512 || TM_COLS == 256, "TMEM allocation must be a power of two");
     const int cnt = *a.count;
     const int m0 = blockIdx.y * kTcBM;
     if (m0 >= cnt) return;
@@ -167,7 +175,8 @@ rc_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
             // instruction descriptor (cute UMMA::InstrDescriptor): c_format F32 = 1 at [4,6); a/b format F16 = 0; K-major both;
             // n_dim = N >> 3 at [17,23); m_dim = M >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-            const uint32_t d_main = tmem_base, d_corr = tmem_base + BN;
+            const uint32_t d_corr = tmem_base + 3 * BN;
+            int g = 0;                                           // global K-step counter
             for (int kb = 0; kb < KB; ++kb) {
                 const int s = kb % STAGES;
                 const uint32_t ph = (kb / STAGES) & 1;
@@ -177,11 +186,11 @@ rc_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
                 const uint64_t dAhi = make_desc(base), dAlo = make_desc(base + A_BYTES);
                 const uint64_t dWhi = make_desc(base + 2 * A_BYTES), dWlo = make_desc(base + 2 * A_BYTES + W_BYTES);
 #pragma unroll
-                for (int k = 0; k < kTcBK / 16; ++k) {
+                for (int k = 0; k < kTcBK / 16; ++k, ++g) {
                     const uint64_t adv = (uint64_t)(k * 2);      // 16 fp16 = 32 bytes = 2 x 16-byte units
-                    const uint32_t acc = (kb | k) ? 1u : 0u;
-                    tc_mma_f16(d_main, dAhi + adv, dWhi + adv, idesc, acc);
-                    tc_mma_f16(d_corr, dAhi + adv, dWlo + adv, idesc, acc);
+                    const uint32_t d_main = tmem_base + (uint32_t)((g % 3) * BN);
+                    tc_mma_f16(d_main, dAhi + adv, dWhi + adv, idesc, g >= 3 ? 1u : 0u);
+                    tc_mma_f16(d_corr, dAhi + adv, dWlo + adv, idesc, g ? 1u : 0u);
                     tc_mma_f16(d_corr, dAlo + adv, dWhi + adv, idesc, 1u);
                 }
                 tc_commit(smem_u32(&bar_empty[s]));              // frees the stage once these MMAs have read it
@@ -195,25 +204,51 @@ rc_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
         const int mrow = m0 + q * 32 + lane;
         const int row = (mrow < cnt) ? a.rows[mrow] : -1;
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int nmain = (KB * (kTcBK / 16) >= 3) ? 3 : KB * (kTcBK / 16);   // accumulators that were written
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
-            uint32_t vm[32], vc[32];
-            tc_ld32(lane_base + (uint32_t)(c * 32), vm);
-            tc_ld32(lane_base + (uint32_t)(BN + c * 32), vc);
+            uint32_t v0[32], v1[32];
+            float acc[32];
+            tc_ld32(lane_base + (uint32_t)(c * 32), v0);
+            tc_ld32(lane_base + (uint32_t)(3 * BN + c * 32), v1);
             tc_ld_wait();
-            if (row >= 0) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int n = n0 + c * 32 + u * 4;
-                    const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
-                    const float gi = fmaf(__uint_as_float(vc[u * 4 + 0]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 0])) + b.x;
-                    const float gf = fmaf(__uint_as_float(vc[u * 4 + 1]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 1])) + b.y;
-                    const float gg = fmaf(__uint_as_float(vc[u * 4 + 2]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 2])) + b.z;
-                    const float go = fmaf(__uint_as_float(vc[u * 4 + 3]), 4.8828125e-4f, __uint_as_float(vm[u * 4 + 3])) + b.w;
-                    const size_t idx = (size_t)row * a.H + (n >> 2);
-                    const float cn = fmaf(sigm(gf), a.C[idx], sigm(gi) * tanhf(gg));
-                    a.C[idx] = cn;
-                    a.Hout[idx] = sigm(go) * tanhf(cn);
+            for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v0[e]);
+            if (nmain > 1) {
+                tc_ld32(lane_base + (uint32_t)(BN + c * 32), v0);
+                tc_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
+            }
+            if (nmain > 2) {
+                tc_ld32(lane_base + (uint32_t)(2 * BN + c * 32), v0);
+                tc_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] = fmaf(__uint_as_float(v1[e]), 4.8828125e-4f, acc[e]);    // + corr * 2^-11
+            if (row >= 0) {
+                if (LSTM) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int n = n0 + c * 32 + u * 4;
+                        const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
+                        const size_t idx = (size_t)row * a.H + (n >> 2);
+                        const float cn = fmaf(sigm(acc[u * 4 + 1] + b.y), a.C[idx], sigm(acc[u * 4 + 0] + b.x) * tanhf(acc[u * 4 + 2] + b.z));
+                        a.C[idx] = cn;
+                        a.Hout[idx] = sigm(acc[u * 4 + 3] + b.w) * tanhf(cn);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int n = n0 + c * 32 + e;
+                        if (n < a.N) {
+                            float y = acc[e] + a.bias[n];
+                            if (a.relu) y = fmaxf(y, 0.f);
+                            a.Y[(size_t)row * a.ldy + n] = y;
+                        }
+                    }
                 }
             }
         }
@@ -227,16 +262,17 @@ rc_lstm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
 
 // Gather the rows of a list from the two K segments, split every fp32 into (hi, lo) fp16 halves, write dense [*, K] rows.
 __global__ void __launch_bounds__(256) rc_split_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ X2, int ldx2,
-                                                             int K1, int K2, const int* __restrict__ rows, const int* __restrict__ count,
-                                                             __half* __restrict__ Ahi, __half* __restrict__ Alo) {
+                                                             int K1, int K2, int Kout, const int* __restrict__ rows,
+                                                             const int* __restrict__ count, __half* __restrict__ Ahi, __half* __restrict__ Alo) {
     const int cnt = *count;
-    const int K = K1 + K2, q4 = K >> 2;
+    const int K = K1 + K2, q4 = Kout >> 2;
     const long long total = (long long)cnt * q4;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         const int i = (int)(e / q4), k = (int)(e % q4) * 4;
         const int r = rows[i];
-        const float4 v = (k < K1) ? *reinterpret_cast<const float4*>(X + (size_t)r * ldx + k)
-                                  : *reinterpret_cast<const float4*>(X2 + (size_t)r * ldx2 + (k - K1));
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < K1) v = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + k);
+        else if (k < K) v = *reinterpret_cast<const float4*>(X2 + (size_t)r * ldx2 + (k - K1));
         const float x[4] = {v.x, v.y, v.z, v.w};
         __half hi[4], lo[4];
 #pragma unroll
@@ -244,8 +280,8 @@ __global__ void __launch_bounds__(256) rc_split_rows_kernel(const float* __restr
             hi[j] = __float2half_rn(x[j]);
             lo[j] = __float2half_rn((x[j] - __half2float(hi[j])) * 2048.f);
         }
-        __half2* ph = reinterpret_cast<__half2*>(Ahi + (size_t)i * K + k);
-        __half2* pl = reinterpret_cast<__half2*>(Alo + (size_t)i * K + k);
+        __half2* ph = reinterpret_cast<__half2*>(Ahi + (size_t)i * Kout + k);
+        __half2* pl = reinterpret_cast<__half2*>(Alo + (size_t)i * Kout + k);
         ph[0] = __halves2half2(hi[0], hi[1]); ph[1] = __halves2half2(hi[2], hi[3]);
         pl[0] = __halves2half2(lo[0], lo[1]); pl[1] = __halves2half2(lo[2], lo[3]);
     }
@@ -295,40 +331,53 @@ void rc_tc_split_host(const float* w, size_t n, std::vector<uint16_t>& hi, std::
     }
 }
 
-int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1, int K2, const int* rows, const int* count, int B,
-                     void* Ahi, void* Alo, void* stream) {
-    const long long work = (long long)B * ((K1 + K2) / 4);
+int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1, int K2, int Kout, const int* rows, const int* count,
+                     int B, void* Ahi, void* Alo, void* stream) {
+    const long long work = (long long)B * (Kout / 4);
     const int grid = (int)std::min<long long>(rc_cdiv(work, 256), 148 * 8);
-    RC_LAUNCH(rc_split_rows_kernel, grid, 256, 0, stream, X, ldx, X2, ldx2, K1, K2, rows, count, (__half*)Ahi, (__half*)Alo);
+    RC_LAUNCH(rc_split_rows_kernel, grid, 256, 0, stream, X, ldx, X2, ldx2, K1, K2, Kout, rows, count, (__half*)Ahi, (__half*)Alo);
     RC_CHECK_LAUNCH();
     return RC_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool LSTM>
 int launch_tc(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo, const TcArgs& a,
-              int B, void* stream) {
+              int n_total, int B, void* stream) {
     constexpr int SMEM = STAGES * (2 * kTcBM * kTcBK * 2 + 2 * BN * kTcBK * 2) + 1024;
     static bool attr_set = false;
     if (!attr_set) {
-        RC_CUDA(cudaFuncSetAttribute(rc_lstm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        RC_CUDA(cudaFuncSetAttribute(rc_tc_kernel<BN, STAGES, LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr_set = true;
     }
-    dim3 grid(4 * a.H / BN, rc_cdiv(B, kTcBM));
-    RC_LAUNCH((rc_lstm_tc_kernel<BN, STAGES>), grid, kTcThreads, SMEM, stream, *(const CUtensorMap*)mAhi, *(const CUtensorMap*)mAlo,
+    dim3 grid(rc_cdiv(n_total, BN), rc_cdiv(B, kTcBM));
+    RC_LAUNCH((rc_tc_kernel<BN, STAGES, LSTM>), grid, kTcThreads, SMEM, stream, *(const CUtensorMap*)mAhi, *(const CUtensorMap*)mAlo,
               *(const CUtensorMap*)mWhi, *(const CUtensorMap*)mWlo, a);
     RC_CHECK_LAUNCH();
     return RC_OK;
 }
 
-int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
-                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream) {
-    TcArgs a;
-    a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
+static int tc_stages() {
     static int stages = 0;
     if (!stages) {
         const char* e = getenv("RC_TC_STAGES");       // tuning knob (2 or 3 ring stages of 64 KB)
         stages = (e && atoi(e) == 2) ? 2 : 3;
     }
-    if (stages == 2) return launch_tc<RC_TC_BN, 2>(mAhi, mAlo, mWhi, mWlo, a, B, stream);
-    return launch_tc<RC_TC_BN, 3>(mAhi, mAlo, mWhi, mWlo, a, B, stream);
+    return stages;
+}
+
+int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream) {
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
+    if (tc_stages() == 2) return launch_tc<RC_TC_BN, 2, true>(mAhi, mAlo, mWhi, mWlo, a, 4 * H, B, stream);
+    return launch_tc<RC_TC_BN, 3, true>(mAhi, mAlo, mWhi, mWlo, a, 4 * H, B, stream);
+}
+
+int rc_tc_linear(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                 const float* bias, float* Y, int ldy, int N, int K, int relu, const int* rows, const int* count, int B, void* stream) {
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bias = bias; a.Y = Y; a.ldy = ldy; a.N = N; a.relu = relu; a.rows = rows; a.count = count; a.K = K;
+    return launch_tc<RC_TC_BN, 3, false>(mAhi, mAlo, mWhi, mWlo, a, N, B, stream);
 }

@@ -12,9 +12,12 @@ struct alignas(64) RcTensorMap { unsigned char opaque[128]; };   // == CUtensorM
 int rc_tc_make_map(RcTensorMap* out, const void* base, long long rows, int K, int box_rows);
 // fp32 -> (hi, lo) fp16 halves with lo pre-scaled by 2^11
 void rc_tc_split_host(const float* w, size_t n, std::vector<uint16_t>& hi, std::vector<uint16_t>& lo);
-// gather list rows from [X | X2], split to fp16 halves, write dense [*, K1+K2]
-int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1, int K2, const int* rows, const int* count, int B,
-                     void* Ahi, void* Alo, void* stream);
+// gather list rows from [X | X2], split to fp16 halves, write dense [*, Kout] (zero beyond K1+K2; Kout multiple of 64)
+int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1, int K2, int Kout, const int* rows, const int* count,
+                     int B, void* Ahi, void* Alo, void* stream);
+// plain linear layer Y = act(A W^T + b) on the tensor cores (W rows padded to a multiple of RC_TC_BN, K to 64)
+int rc_tc_linear(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                 const float* bias, float* Y, int ldy, int N, int K, int relu, const int* rows, const int* count, int B, void* stream);
 // fused LSTM layer on the tensor cores over the rows of a list
 int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
                      const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream);
