@@ -149,6 +149,27 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* h_j2dc, const 
                              const int32_t* h_lengths, const float* h_first_tran, const int32_t* h_row_flags,
                              float* h_pose, float* h_tran, int use_graph, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * SMPLify objective — net/smplify/losses.py:23-91 evaluated as in temporal_smplify.py:153-165, with the analytic
+ * gradient that replaces the reference's autograd pass.  The optimiser (torch.optim.LBFGS, a third-party class the
+ * reference calls at temporal_smplify.py:151) stays on the host side.
+ *   rc_smplify_create: GMM prior constants as prior.py:113-143 builds them: means [8,69], precisions [8,69,69],
+ *                      log(nll_weights) [8] (HOST float32); t = frames per sequence.
+ *   rc_smplify_loss_grad: d_pose [t,72] axis-angle (rodrigues 0 = batch_rodrigues, temporal_smplify.py:25-59;
+ *                      1 = axis_angle_to_rotation_matrix, angular.py:221-233) or [t,24,3,3] matrices (rodrigues 2,
+ *                      value-only, get_fitting_loss temporal_smplify.py:198-220); d_tran [t,3]; d_j2d [t,33,2] pixels;
+ *                      d_conf [t,33]; d_cam_k [3,3]; d_ref3d [t,33,3] (the detached initial points); d_imu_aa [t,6,3]
+ *                      (axis-angles of imu_ori).  Outputs: d_loss [1] (output='sum'), d_grad_pose [t,72], d_grad_tran
+ *                      [t,3] (both or neither), d_reproj [t,33] (output='reprojection') or NULL.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct rc_smplify rc_smplify;
+int rc_smplify_create(rc_smplify** out, const rc_model* model, const float* h_means, const float* h_precisions,
+                      const float* h_log_nll_weights, int32_t t);
+void rc_smplify_destroy(rc_smplify* s);
+int rc_smplify_loss_grad(rc_smplify* s, const float* d_pose, const float* d_tran, const float* d_j2d, const float* d_conf,
+                         const float* d_cam_k, const float* d_ref3d, const float* d_imu_aa, int rodrigues, float* d_loss,
+                         float* d_grad_pose, float* d_grad_tran, float* d_reproj, void* stream);
+
 /* Test tap: one fused LSTM layer of sub-net `ni` (0..5 = rnn2,3,4,6,7,8), layer 0/1, on caller-provided device data for
  * all b rows of the state: d_x [b,H], d_hprev [b,H], d_c [b,H] (in place), d_hout [b,H]; mode as rc_net_set_gemm_mode. */
 int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* d_x, const float* d_hprev, float* d_c,

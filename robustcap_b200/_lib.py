@@ -99,15 +99,13 @@ _SIGS = {
     'rc_forward_sequence_host': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     'rc_state_debug_output': (i32, [vp, i32, vp, vp]),
     'rc_state_debug_lstm': (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
-    'rc_profile_enable': (i32, [vp, i32]),
-    'rc_profile_collect': (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]),
-}
-# entry points added by later source files; bound when present
-_OPTIONAL_SIGS = {
     'rc_smplify_create': (i32, [ctypes.POINTER(vp), vp, vp, vp, vp, i32]),
     'rc_smplify_destroy': (None, [vp]),
     'rc_smplify_loss_grad': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'rc_profile_enable': (i32, [vp, i32]),
+    'rc_profile_collect': (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]),
 }
+_OPTIONAL_SIGS = {}
 
 
 def exported_symbols():
