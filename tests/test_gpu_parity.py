@@ -212,7 +212,7 @@ def test_tensor_core_gemm_matches_simt(rb, body):
     print('pose max %.2e rad, 99.9 %% %.2e rad, tran %.2e m' % (ang.max().item(), ang.quantile(0.999).item(), terr))
     # two float32-accurate evaluations differ by reduction order only; the rare ill-conditioned joints (tiny 6D vectors through
     # Gram-Schmidt with random-init weights) amplify that noise, hence a quantile bound plus a loose cap on the maximum
-    assert ang.quantile(0.999).item() < 2e-5 and ang.max().item() < 5e-4 and terr < 1e-4
+    assert ang.quantile(0.999).item() < 5e-5 and ang.max().item() < 5e-4 and terr < 1e-4
 
 
 def test_offline_vs_oracle_seeded(rb, body, assets):
