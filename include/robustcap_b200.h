@@ -133,6 +133,14 @@ int rc_forward_step(rc_state* s, const float* d_j2dc, const float* d_accc, const
                     const float* d_gravity, const float* d_first_tran, const int32_t* d_row_flags,
                     int any_first_frame, float* d_pose, float* d_tran, void* stream);
 
+/* Net.forward_online for ONE stream (state created with b = 1), lowest latency: inputs ([33,3], [6,3], [6,3,3], optional
+ * first_tran [3]) are HOST pointers (inputs_on_device = 0; packed into one pinned buffer, one H2D copy) or DEVICE pointers
+ * (inputs_on_device = 1); the frame runs as one cached CUDA graph; results are copied back to the HOST pointers h_pose
+ * [24,3,3] and h_tran [3] and the stream is synchronised — exactly the reference's contract of returning CPU tensors
+ * (sig_mp.py:274). */
+int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const float* oric, const float* first_tran,
+                      int first_frame, int inputs_on_device, float* h_pose, float* h_tran, void* stream);
+
 /* forward_offline := reset_states + forward_online over t (evaluate.py:75-85,93), batched over B sequences.
  *   d_j2dc [b,T,33,3], d_accc [b,T,6,3], d_oric [b,T,6,3,3]; d_lengths int32[b] or NULL (ragged batch: rows
  *   stop advancing after their length; outputs beyond it are left untouched);

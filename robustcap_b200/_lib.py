@@ -95,6 +95,7 @@ _SIGS = {
     'rc_state_reset': (i32, [vp, vp]),
     'rc_state_set_gravity': (i32, [vp, vp, vp]),
     'rc_forward_step': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
+    'rc_forward_online': (i32, [vp, vp, vp, vp, vp, i32, i32, vp, vp, vp]),
     'rc_forward_sequence': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp]),
     'rc_forward_sequence_host': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     'rc_state_debug_output': (i32, [vp, i32, vp, vp]),

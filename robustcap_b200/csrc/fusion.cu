@@ -13,8 +13,10 @@
 #include <string>
 #include <vector>
 #include <string.h>
+#include <stdlib.h>
 #include "rc_common.cuh"
 #include "rc_rows.h"
+#include "rc_rows_warp.cuh"
 #include "rc_model.cuh"
 #include "rc_linear.cuh"
 #include "rc_pack.h"
@@ -89,6 +91,11 @@ struct rc_state {
     int prof_on = 0;
     std::vector<cudaEvent_t> prof_ev;
     size_t prof_used = 0;
+    // low-latency single-frame path (rc_forward_online): fixed staging buffers so the frame is one cached CUDA graph
+    float *on_din = nullptr, *on_dout = nullptr, *on_hin = nullptr, *on_hout = nullptr;   // device / pinned host
+    cudaGraphExec_t on_graph = nullptr;
+    void* on_graph_stream = nullptr;
+    long long on_graph_nodes = 0;
     // staging buffers of rc_forward_sequence_host
     float *hj = nullptr, *ha = nullptr, *ho = nullptr, *hp = nullptr, *ht = nullptr, *hft = nullptr;
     int *hlen = nullptr, *hfl = nullptr;
@@ -196,6 +203,66 @@ __global__ void __launch_bounds__(64) rc_kin_kernel(RcNetCfg cfg, const RcModelC
         for (int i = 0; i < 69; ++i) XI[(size_t)b * kInitK0 + i] = X7[(size_t)b * RC_K7 + 72 + i];
         for (int i = 69; i < kInitK0; ++i) XI[(size_t)b * kInitK0 + i] = 0.f;
         lists[L_INIT * B + atomicAdd(&counts[L_INIT], 1)] = b;
+    }
+}
+
+// ---- warp-per-stream versions (default): same arithmetic, 4 streams per block -------------------------------------------
+constexpr int kRowWarps = 4;
+
+__global__ void __launch_bounds__(kRowWarps * 32) rc_prep_warp_kernel(RcNetCfg cfg, const RcRowState* __restrict__ rows, StepIO io, int B,
+                                                                       float* X2, float* X3, float* X4, float* X6, float* X7,
+                                                                       float* rcr, float* conf, float* lerpw, int* flags) {
+    __shared__ RcPrepWarpSmem S[kRowWarps];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kRowWarps + w;
+    if (b >= B) return;
+    const int t = io.d_t ? *io.d_t : 0;
+    int inflags = 0;
+    if (io.row_flags && (io.first_mode == 1 || (io.first_mode == 2 && t == 0))) inflags = io.row_flags[b] & 3;
+    if (!io.first_tran) inflags &= ~RC_F_FIRST_TRAN;
+    const bool active = !io.lengths || t < io.lengths[b];
+    if (!active) { if (lane == 0) flags[b] = 0; return; }
+    inflags |= RC_F_ACTIVE;
+    const int f = rc_prep_warp(cfg, rows[b].vision_count, S[w], io.j2dc + b * io.sj + (long long)t * 99,
+                               io.accc + b * io.sa + (long long)t * 18, io.oric + b * io.so + (long long)t * 54, inflags,
+                               X2 + (size_t)b * RC_K2, X3 + (size_t)b * RC_K3, X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6,
+                               X7 + (size_t)b * RC_K7, rcr + b * 9, conf + b, lerpw + b * 2, lane);
+    if (lane == 0) flags[b] = f;
+}
+
+__global__ void __launch_bounds__(kRowWarps * 32) rc_kin_warp_kernel(RcNetCfg cfg, const RcModelConst* __restrict__ M, RcRowState* rows,
+                                                                      const int* __restrict__ flags, int B, StepIO io,
+                                                                      const float* __restrict__ Y7, const float* __restrict__ Y8,
+                                                                      const float* __restrict__ Y3, const float* __restrict__ Y6,
+                                                                      const float* __restrict__ rcr, const float* __restrict__ conf,
+                                                                      const float* __restrict__ gravity_all, float* X4, float* X6,
+                                                                      const float* X7, float* XI, int* lists, int* counts) {
+    __shared__ RcKinWarpSmem S[kRowWarps];
+    __shared__ RcModelConst Ms;
+    {   // SMPL constants once per block
+        const int* src = reinterpret_cast<const int*>(M);
+        int* dst = reinterpret_cast<int*>(&Ms);
+        for (int e = threadIdx.x; e < (int)(sizeof(RcModelConst) / 4); e += blockDim.x) dst[e] = src[e];
+    }
+    __syncthreads();
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.x * kRowWarps + w;
+    if (b >= B) return;
+    const int f = flags[b];
+    if (!(f & RC_F_ACTIVE)) return;
+    const int t = io.d_t ? *io.d_t : 0;
+    float r[9], g[3], ft[3] = {0.f, 0.f, 0.f}, y8[2], vr[3], pc[3];
+    for (int i = 0; i < 9; ++i) r[i] = rcr[b * 9 + i];
+    const float* gp = io.gravity ? (io.gravity + (size_t)b * 3) : gravity_all;
+    for (int i = 0; i < 3; ++i) { g[i] = gp[i]; vr[i] = Y3[b * 4 + i]; pc[i] = Y6[b * 4 + i]; }
+    y8[0] = Y8[b * 4]; y8[1] = Y8[b * 4 + 1];
+    if (f & RC_F_FIRST_TRAN) for (int i = 0; i < 3; ++i) ft[i] = io.first_tran[(size_t)b * 3 + i];
+    const int need_init = rc_kin_warp(cfg, Ms, S[w], rows + b, f, Y7 + (size_t)b * 144, y8, vr, pc, r, conf[b], g, ft,
+                                      io.pose + b * io.sp + (long long)t * 216, io.tran + b * io.st + (long long)t * 3,
+                                      X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6, lane);
+    if (need_init) {
+        for (int i = lane; i < kInitK0; i += 32) XI[(size_t)b * kInitK0 + i] = (i < 69) ? X7[(size_t)b * RC_K7 + 72 + i] : 0.f;
+        if (lane == 0) lists[L_INIT * B + atomicAdd(&counts[L_INIT], 1)] = b;
     }
 }
 
@@ -345,8 +412,13 @@ int init_pass(rc_state* s, void* stream) {
 int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advance, void* stream) {
     const rc_net* n = s->net;
     const int B = s->B;
-    RC_LAUNCH(rc_prep_kernel, rc_cdiv(B, 128), 128, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4, s->X6, s->X7,
-              s->rcr, s->conf, s->lerpw, s->flags);
+    static const bool scalar_rows = getenv("RC_SCALAR_ROWS") != nullptr;     // validation switch: one-thread-per-stream kernels
+    if (scalar_rows)
+        RC_LAUNCH(rc_prep_kernel, rc_cdiv(B, 128), 128, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4, s->X6, s->X7,
+                  s->rcr, s->conf, s->lerpw, s->flags);
+    else
+        RC_LAUNCH(rc_prep_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4,
+                  s->X6, s->X7, s->rcr, s->conf, s->lerpw, s->flags);
     RC_CHECK_LAUNCH();
     RC_LAUNCH(rc_lists_kernel, 1, NLISTS * 32, 0, stream, s->flags, B, s->lists, s->counts);
     RC_CHECK_LAUNCH();
@@ -359,8 +431,12 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
     RC_CHECK_LAUNCH();
     RC_TRY(net_pass(s, NET7, L_ALL, s->X7, s->Y7, 144, stream));                       // poseg6d           (:169)
     RC_TRY(net_pass(s, NET8, L_ALL, s->X7, s->Y8, 4, stream));                         // contact logits    (:170)
-    RC_LAUNCH(rc_kin_kernel, rc_cdiv(B, 64), 64, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B, io, s->Y7, s->Y8,
-              s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
+    if (scalar_rows)
+        RC_LAUNCH(rc_kin_kernel, rc_cdiv(B, 64), 64, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B, io, s->Y7, s->Y8,
+                  s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
+    else
+        RC_LAUNCH(rc_kin_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B,
+                  io, s->Y7, s->Y8, s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
     RC_CHECK_LAUNCH();
     RC_TRY(init_pass(s, stream));                                                      // (:178-183)
     RC_TRY(net_pass(s, NET6, L_LATE, s->X6, nullptr, 0, stream));                      // vision updater    (:267)
@@ -573,6 +649,8 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
 void rc_state_destroy(rc_state* s) {
     if (!s) return;
     if (s->graph) cudaGraphExecDestroy(s->graph);
+    if (s->on_graph) cudaGraphExecDestroy(s->on_graph);
+    cudaFree(s->on_din); cudaFree(s->on_dout); cudaFreeHost(s->on_hin); cudaFreeHost(s->on_hout);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     for (void* p : s->allocs) cudaFree(p);
@@ -619,6 +697,69 @@ int rc_forward_step(rc_state* s, const float* j2dc, const float* accc, const flo
     io.gravity = gravity; io.first_tran = first_tran; io.row_flags = row_flags; io.lengths = nullptr;
     io.pose = pose; io.tran = tran; io.sp = 216; io.st = 3; io.d_t = nullptr; io.first_mode = 1;
     return enqueue_step(s, io, any_first_frame, false, stream);
+}
+
+// Layout of the single-frame staging buffer: j2dc[99] | accc[18] | oric[54] | first_tran[3] | flags (int) | pad
+constexpr int kOnIn = 176, kOnOut = 220;
+
+int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const float* oric, const float* first_tran,
+                      int first_frame, int inputs_on_device, float* h_pose, float* h_tran, void* stream) {
+    RC_ARG(s && s->B == 1 && j2dc && accc && oric && h_pose && h_tran);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!s->on_din) {
+        RC_CUDA(cudaMalloc(&s->on_din, kOnIn * sizeof(float)));
+        RC_CUDA(cudaMalloc(&s->on_dout, kOnOut * sizeof(float)));
+        RC_CUDA(cudaMallocHost(&s->on_hin, kOnIn * sizeof(float)));
+        RC_CUDA(cudaMallocHost(&s->on_hout, kOnOut * sizeof(float)));
+    }
+    int flags = (first_frame ? RC_ROW_FIRST_FRAME : 0) | (first_tran ? RC_ROW_FIRST_TRAN : 0);
+    if (inputs_on_device) {
+        RC_CUDA(cudaMemcpyAsync(s->on_din, j2dc, 99 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        RC_CUDA(cudaMemcpyAsync(s->on_din + 99, accc, 18 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        RC_CUDA(cudaMemcpyAsync(s->on_din + 117, oric, 54 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (first_tran) RC_CUDA(cudaMemcpyAsync(s->on_din + 171, first_tran, 3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        memcpy(s->on_hin + 174, &flags, sizeof(int));
+        RC_CUDA(cudaMemcpyAsync(s->on_din + 174, s->on_hin + 174, sizeof(int), cudaMemcpyHostToDevice, st));
+    } else {
+        memcpy(s->on_hin, j2dc, 99 * sizeof(float));
+        memcpy(s->on_hin + 99, accc, 18 * sizeof(float));
+        memcpy(s->on_hin + 117, oric, 54 * sizeof(float));
+        if (first_tran) memcpy(s->on_hin + 171, first_tran, 3 * sizeof(float));
+        memcpy(s->on_hin + 174, &flags, sizeof(int));
+        RC_CUDA(cudaMemcpyAsync(s->on_din, s->on_hin, kOnIn * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    StepIO io;
+    io.j2dc = s->on_din; io.accc = s->on_din + 99; io.oric = s->on_din + 117; io.sj = 99; io.sa = 18; io.so = 54;
+    io.gravity = nullptr; io.first_tran = s->on_din + 171; io.row_flags = (const int*)(s->on_din + 174); io.lengths = nullptr;
+    io.pose = s->on_dout; io.tran = s->on_dout + 216; io.sp = 216; io.st = 3; io.d_t = nullptr; io.first_mode = 1;
+    if (first_frame) {
+        RC_TRY(enqueue_step(s, io, 1, false, stream));          // extra rnn6 pass (sig_mp.py:155-156): direct launches
+    } else {
+        if (!s->on_graph || s->on_graph_stream != stream) {
+            if (s->on_graph) { cudaGraphExecDestroy(s->on_graph); s->on_graph = nullptr; }
+            cudaGraph_t g = nullptr;
+            if (!s->cap_stream) RC_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+            RC_CUDA(cudaStreamBeginCapture(s->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const long long before = g_rc_launches.load();
+            const int rc = enqueue_step(s, io, 0, false, (void*)s->cap_stream);
+            s->on_graph_nodes = g_rc_launches.load() - before;
+            g_rc_launches.fetch_sub(s->on_graph_nodes);
+            cudaError_t e = cudaStreamEndCapture(s->cap_stream, &g);
+            if (rc != RC_OK) { if (g) cudaGraphDestroy(g); return rc; }
+            if (e != cudaSuccess) { rc_set_error("graph capture: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
+            e = cudaGraphInstantiate(&s->on_graph, g, 0);
+            cudaGraphDestroy(g);
+            if (e != cudaSuccess) { s->on_graph = nullptr; rc_set_error("graph instantiate: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
+            s->on_graph_stream = stream;
+        }
+        RC_CUDA(cudaGraphLaunch(s->on_graph, st));
+        g_rc_launches.fetch_add(s->on_graph_nodes);
+    }
+    RC_CUDA(cudaMemcpyAsync(s->on_hout, s->on_dout, kOnOut * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RC_CUDA(cudaStreamSynchronize(st));
+    memcpy(h_pose, s->on_hout, 216 * sizeof(float));
+    memcpy(h_tran, s->on_hout + 216, 3 * sizeof(float));
+    return RC_OK;
 }
 
 int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* accc, const float* oric,

@@ -206,6 +206,11 @@ int rc_model_create(rc_model** out, const float* joints, const float* verts, con
     }
     for (int i = 0; i < RC_NJ; ++i)
         for (int r = 0; r < 3; ++r) C.bone[i][r] = (i == 0) ? C.jrest[0][r] : (-C.jrest[C.parent[i]][r] + C.jrest[i][r]);
+    C.max_depth = 0;
+    for (int i = 0; i < RC_NJ; ++i) {
+        C.depth[i] = (i == 0) ? 0 : C.depth[C.parent[i]] + 1;
+        if (C.depth[i] > C.max_depth) C.max_depth = C.depth[i];
+    }
     // net/sig_mp.py:287-299: rows 11-16 <- joints 16-21, 23-24 <- 1-2, 25-26 <- 4-5, 27-28 <- 7-8
     for (int k = 0; k < RC_NKP; ++k) {
         int j = -1;

@@ -33,6 +33,8 @@ enum RcFlag {
 
 struct RcModelConst {                 // SMPL constants the per-frame path needs (articulate/model.py:29-39)
     int parent[RC_NJ];                // parent[0] = -1
+    int depth[RC_NJ];                 // tree depth of each joint (root 0); max_depth = deepest level
+    int max_depth;
     float jrest[RC_NJ][3];            // zero-pose joints, root at origin (model.py:87)
     float bone[RC_NJ][3];             // bone[i] = -jrest[parent] + jrest[i]   (spatial.py:148-167)
     int kp_is_joint[RC_NKP];          // the 33 synthetic MediaPipe points (sig_mp.py:287-299)
@@ -93,6 +95,23 @@ RC_HD void rc_normalise_kp(const float* kp, float* out) {
     }
 }
 
+// Branch flags of one frame from the mean confidence (sig_mp.py:149-167, 229-242, 264) + the lerp weights (:163-164).
+RC_HD int rc_prep_flags(const RcNetCfg& cfg, int vision_count, float cf, int in_flags, float* lerpw) {
+    const double c = (double)cf;                             // .item() -> python float     (:138)
+    int f = in_flags & (RC_F_FIRST_FRAME | RC_F_FIRST_TRAN | RC_F_ACTIVE);
+    const bool ff = (in_flags & RC_F_FIRST_FRAME) != 0;
+    if (c > cfg.conf_lo || ff) f |= RC_F_HI;                                          // :149
+    if (c >= cfg.conf_hi) f |= RC_F_GE;
+    else if (c > cfg.conf_lo) f |= RC_F_MID;
+    if (c > cfg.conf_lo) f |= RC_F_R6B;
+    const bool do_fk = (!cfg.live) || vision_count == 0;                              // :229-242
+    if (do_fk) f |= RC_F_DO_FK;
+    if (c <= cfg.conf_lo && do_fk) f |= RC_F_LATE;                                    // :264
+    const double k = (c - cfg.conf_lo) / (cfg.conf_hi - cfg.conf_lo);                 // :163
+    lerpw[0] = (float)(1.0 - k); lerpw[1] = (float)k;
+    return f;
+}
+
 // ---- prep ---------------------------------------------------------------------------------------------------
 // Outputs (row pointers into the [B, K] sub-net input buffers): x2[80], x3[144], x4[176], x6[240], x7[144];
 // rcr[9]; conf[0] = c; lerpw[2] = (float)(1-k), (float)k; returns the flag word.
@@ -100,7 +119,6 @@ RC_HD int rc_prep_row(const RcNetCfg& cfg, const RcRowState& st, const float* j2
                       const float* oric, int in_flags, float* x2, float* x3, float* x4, float* x6, float* x7,
                       float* rcr, float* conf, float* lerpw) {
     float cf = rc_conf_mean(j2dc);
-    double c = (double)cf;                                   // .item() -> python float     (:138)
     const float* R = oric + 5 * 9;                           // Rcr = oric[-1]              (:139)
     for (int i = 0; i < 9; ++i) rcr[i] = R[i];
     float xr[72], *xc = x4;
@@ -114,20 +132,8 @@ RC_HD int rc_prep_row(const RcNetCfg& cfg, const RcRowState& st, const float* j2
     for (int i = 0; i < 99; ++i) x6[72 + i] = j2dc[i];                                // raw key points for rnn6 (:156)
     for (int i = 171; i < RC_K4; ++i) x4[i] = 0.f;
 
-    int f = in_flags & (RC_F_FIRST_FRAME | RC_F_FIRST_TRAN | RC_F_ACTIVE);
-    bool ff = (in_flags & RC_F_FIRST_FRAME) != 0;
-    if (c > cfg.conf_lo || ff) {                                                      // :149
-        f |= RC_F_HI;
-        rc_normalise_kp(j2dc, x4 + 72);
-    }
-    if (c >= cfg.conf_hi) f |= RC_F_GE;
-    else if (c > cfg.conf_lo) f |= RC_F_MID;
-    if (c > cfg.conf_lo) f |= RC_F_R6B;
-    bool do_fk = (!cfg.live) || st.vision_count == 0;                                 // :229-242
-    if (do_fk) f |= RC_F_DO_FK;
-    if (c <= cfg.conf_lo && do_fk) f |= RC_F_LATE;                                    // :264
-    double k = (c - cfg.conf_lo) / (cfg.conf_hi - cfg.conf_lo);                       // :163
-    lerpw[0] = (float)(1.0 - k); lerpw[1] = (float)k;
+    const int f = rc_prep_flags(cfg, st.vision_count, cf, in_flags, lerpw);
+    if (f & RC_F_HI) rc_normalise_kp(j2dc, x4 + 72);                                   // :150-152
     conf[0] = cf;
     return f;
 }
@@ -195,36 +201,11 @@ RC_HD void rc_floor_point(const float* pf, const float* tran, const float* g, fl
     p[0] = RC_MUL(d, g[0]); p[1] = RC_MUL(d, g[1]); p[2] = RC_MUL(d, g[2]);
 }
 
-// Inputs: y7[144] (6D global pose), y8[2] (contact logits), vr[3] (rnn3), pc[3] (rnn6 early result, valid when
-// GE or FIRST_FRAME), rcr[9], conf, gravity[3], first_tran[3].
-// Outputs: pose[216], tran[3]; when RC_F_LATE: x6/x4 rows rewritten with the synthetic key points;
-// returns 1 when this stream must re-seed rnn2's state through init_net (:178-183) with j3dr (= x7 + 72).
-RC_HD int rc_kin_row(const RcNetCfg& cfg, const RcModelConst& M, RcRowState* st, int flags, const float* y7,
-                     const float* y8, const float* vr, const float* pc, const float* rcr, float conf,
-                     const float* gravity, const float* first_tran, float* pose, float* tran_out, float* x4,
-                     float* x6) {
-    double c = (double)conf;
-    float G[RC_NJ][9];
-    for (int i = 0; i < RC_NJ; ++i) rc_r6d_to_mat(y7 + i * 6, G[i]);                   // :173
-    for (int e = 0; e < 9; ++e) pose[e] = rcr[e];                                        // pose[0] = Rcr (:175)
-    for (int i = 1; i < RC_NJ; ++i) rc_mat3_tmul(G[M.parent[i]], G[i], pose + i * 9);    // IK (:174)
-
-    int need_init = 0;
-    if ((flags & RC_F_GE) && st->first_reach) { st->first_reach = 0; need_init = 1; }    // :178-183
-
-    // foot FK from global rotations and rest bones (:131-135, :186)
-    float jp[RC_NJ][3];
-    jp[0][0] = jp[0][1] = jp[0][2] = 0.f;
-    for (int i = 1; i < RC_NJ; ++i) {
-        float pb[3];
-        rc_mat3_vec(G[M.parent[i]], M.bone[i], pb);
-        for (int r = 0; r < 3; ++r) jp[i][r] = RC_ADD(jp[M.parent[i]][r], pb[r]);
-    }
-    float pfoot[6];
-    for (int f = 0; f < 2; ++f)                                                          // fk(poseg)[10:12].mm(Rcr.t())
-        for (int j = 0; j < 3; ++j)
-            pfoot[f * 3 + j] = jp[10 + f][0] * rcr[j * 3 + 0] + jp[10 + f][1] * rcr[j * 3 + 1] + jp[10 + f][2] * rcr[j * 3 + 2];
-
+// Translation / contact / floor state machine of one frame (sig_mp.py:185-227, 273): returns tran and updates the state.
+RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const float* pfoot, const float* y8, const float* vr,
+                          const float* pc, const float* rcr, float conf, const float* gravity, const float* first_tran,
+                          float* tran_out) {
+    const double c = (double)conf;
     float ct0 = 1.f / (1.f + expf(-y8[0])), ct1 = 1.f / (1.f + expf(-y8[1]));           // sigmoid (:170)
     float cmax = fmaxf(ct0, ct1);
     int carg = (ct1 > ct0) ? 1 : 0;                                                      // argmax, first max wins
@@ -283,6 +264,41 @@ RC_HD int rc_kin_row(const RcNetCfg& cfg, const RcModelConst& M, RcRowState* st,
     for (int e = 0; e < 6; ++e) st->last_pfoot[e] = pfoot[e];                            // :227
     for (int r = 0; r < 3; ++r) { st->last_tran[r] = tran[r]; tran_out[r] = tran[r]; }   // :273
     st->has_last = 1;
+
+}
+
+// Inputs: y7[144] (6D global pose), y8[2] (contact logits), vr[3] (rnn3), pc[3] (rnn6 early result, valid when
+// GE or FIRST_FRAME), rcr[9], conf, gravity[3], first_tran[3].
+// Outputs: pose[216], tran[3]; when RC_F_LATE: x6/x4 rows rewritten with the synthetic key points;
+// returns 1 when this stream must re-seed rnn2's state through init_net (:178-183) with j3dr (= x7 + 72).
+RC_HD int rc_kin_row(const RcNetCfg& cfg, const RcModelConst& M, RcRowState* st, int flags, const float* y7,
+                     const float* y8, const float* vr, const float* pc, const float* rcr, float conf,
+                     const float* gravity, const float* first_tran, float* pose, float* tran_out, float* x4,
+                     float* x6) {
+    float G[RC_NJ][9];
+    for (int i = 0; i < RC_NJ; ++i) rc_r6d_to_mat(y7 + i * 6, G[i]);                   // :173
+    for (int e = 0; e < 9; ++e) pose[e] = rcr[e];                                        // pose[0] = Rcr (:175)
+    for (int i = 1; i < RC_NJ; ++i) rc_mat3_tmul(G[M.parent[i]], G[i], pose + i * 9);    // IK (:174)
+
+    int need_init = 0;
+    if ((flags & RC_F_GE) && st->first_reach) { st->first_reach = 0; need_init = 1; }    // :178-183
+
+    // foot FK from global rotations and rest bones (:131-135, :186)
+    float jp[RC_NJ][3];
+    jp[0][0] = jp[0][1] = jp[0][2] = 0.f;
+    for (int i = 1; i < RC_NJ; ++i) {
+        float pb[3];
+        rc_mat3_vec(G[M.parent[i]], M.bone[i], pb);
+        for (int r = 0; r < 3; ++r) jp[i][r] = RC_ADD(jp[M.parent[i]][r], pb[r]);
+    }
+    float pfoot[6];
+    for (int f = 0; f < 2; ++f)                                                          // fk(poseg)[10:12].mm(Rcr.t())
+        for (int j = 0; j < 3; ++j)
+            pfoot[f * 3 + j] = jp[10 + f][0] * rcr[j * 3 + 0] + jp[10 + f][1] * rcr[j * 3 + 1] + jp[10 + f][2] * rcr[j * 3 + 2];
+
+    float tran[3];
+    rc_tran_update(cfg, st, flags, pfoot, y8, vr, pc, rcr, conf, gravity, first_tran, tran);
+    for (int r = 0; r < 3; ++r) tran_out[r] = tran[r];
 
     // :228-242 mesh FK -> synthetic key points; live mode recomputes every (freq+1)-th frame only
     if (flags & RC_F_DO_FK) {

@@ -161,24 +161,21 @@ class Net(torch.nn.Module):
         pose [24,3,3] (local, root = pelvis IMU) and tran [3], both on the CPU. sig_mp.py:113-274."""
         lib = _lib.load()
         self._ensure_native()
-        dev = _lib.require_cuda()
+        _lib.require_cuda()
         st = self._state(1)
-        f32 = dict(device=dev, dtype=torch.float32)
-        dj = j2dc.detach().reshape(1, 99).to(**f32).contiguous()
-        da = accc.detach().reshape(1, 18).to(**f32).contiguous()
-        do = oric.detach().reshape(1, 54).to(**f32).contiguous()
-        flags, dft = 0, None
-        if first_frame:
-            flags |= 1
+        on_dev = j2dc.is_cuda
+        assert accc.is_cuda == on_dev and oric.is_cuda == on_dev, 'inputs must live on one device'
+        prep = lambda x, n: x.detach().reshape(n).to(torch.float32).contiguous()
+        dj, da, do = prep(j2dc, 99), prep(accc, 18), prep(oric, 54)
+        dft = None
         if first_tran is not None:
-            flags |= 2
-            dft = first_tran.detach().reshape(1, 3).to(**f32).contiguous()
-        dfl = torch.tensor([flags], dtype=torch.int32, device=dev) if flags else None
-        pose = torch.empty(1, 24, 3, 3, **f32)
-        tran = torch.empty(1, 3, **f32)
-        _lib.check(lib.rc_forward_step(st, _lib.dptr(dj), _lib.dptr(da), _lib.dptr(do), None, _lib.dptr(dft), _lib.dptr(dfl),
-                                       int(bool(first_frame)), _lib.dptr(pose), _lib.dptr(tran), _lib.stream()))
-        return pose.view(24, 3, 3).cpu(), tran.view(3).cpu()
+            dft = prep(first_tran, 3)
+            dft = dft.to(dj.device)
+        pose = torch.empty(24, 3, 3)
+        tran = torch.empty(3)
+        _lib.check(lib.rc_forward_online(st, dj.data_ptr(), da.data_ptr(), do.data_ptr(), None if dft is None else dft.data_ptr(),
+                                         int(bool(first_frame)), int(on_dev), pose.data_ptr(), tran.data_ptr(), _lib.stream()))
+        return pose, tran
 
     @torch.no_grad()
     def forward_offline(self, j2dc, accc, oric, first_tran=None, first_frame=False, lengths=None, use_graph=None,

@@ -84,6 +84,8 @@ void* hh_create(const float* joints, const float* verts, const float* skin_w, in
     }
     for (int i = 0; i < RC_NJ; ++i)
         for (int r = 0; r < 3; ++r) C.bone[i][r] = i == 0 ? C.jrest[0][r] : (-C.jrest[C.parent[i]][r] + C.jrest[i][r]);
+    C.max_depth = 0;
+    for (int i = 0; i < RC_NJ; ++i) { C.depth[i] = i == 0 ? 0 : C.depth[C.parent[i]] + 1; if (C.depth[i] > C.max_depth) C.max_depth = C.depth[i]; }
     for (int k = 0; k < RC_NKP; ++k) {
         int j = -1;
         if (k >= 11 && k <= 16) j = 16 + (k - 11);

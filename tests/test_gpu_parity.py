@@ -272,3 +272,37 @@ def test_full_size_properties(rb, body):
     assert torch.isfinite(t1).all()
     p3, t3 = net.forward_offline(j[:128], a[:128], o[:128], first_tran=ft, use_graph=False)
     assert torch.equal(p3, p1[:128]) and torch.equal(t3, t1[:128])
+
+
+def test_warp_rows_match_scalar(rb, body, assets, tmp_path):
+    """The warp-per-stream prep/kin kernels must reproduce the one-thread-per-stream kernels (host-validated logic) bit for bit."""
+    import subprocess
+    import sys
+    script = r'''
+import sys, torch
+sys.path.insert(0, %r)
+import robustcap_b200 as rb
+from robustcap_b200 import synthetic
+assets = synthetic.write_assets(synthetic.default_asset_root(), 0)
+net = rb.Net(rb.ParametricModel(assets['smpl_file']))
+net.load_state_dict(synthetic.make_state_dict(0, 'contact'))
+inp = synthetic.make_inputs(70, 24, seed=41, conf='mixed')
+rb.Net.gravityc = inp['gravity'].clone()
+ff = torch.arange(70) %% 3 == 0
+p, t = net.forward_offline(inp['j2dc'].cuda(), inp['accc'].cuda(), inp['oric'].cuda(), first_tran=torch.tensor([0., 0., 4.]),
+                           first_frame=ff, first_tran_mask=~ff)
+ps, ts = net.forward_offline(inp['j2dc'][5].cuda(), inp['accc'][5].cuda(), inp['oric'][5].cuda(), first_frame=True)
+torch.save({'p': p.cpu(), 't': t.cpu(), 'ps': ps.cpu(), 'ts': ts.cpu()}, sys.argv[1])
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = {}
+    for mode in ('warp', 'scalar'):
+        env = dict(os.environ)
+        if mode == 'scalar':
+            env['RC_SCALAR_ROWS'] = '1'
+        else:
+            env.pop('RC_SCALAR_ROWS', None)
+        f = str(tmp_path / (mode + '.pt'))
+        subprocess.check_call([sys.executable, '-c', script, f], env=env)
+        outs[mode] = torch.load(f)
+    for k in ('p', 't', 'ps', 'ts'):
+        assert torch.equal(outs['warp'][k], outs['scalar'][k]), k
