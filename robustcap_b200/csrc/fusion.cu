@@ -72,10 +72,14 @@ struct rc_state {
     float *Y3 = nullptr, *Y6 = nullptr, *Y7 = nullptr, *Y8 = nullptr, *Ydump = nullptr;
     float *I1 = nullptr, *I2 = nullptr, *I3 = nullptr;
     float *rcr = nullptr, *conf = nullptr, *lerpw = nullptr, *gravity = nullptr;
-    uint16_t *Ahi = nullptr, *Alo = nullptr;     // [Bpad, 2*Hmax] split activations (tensor-core path)
-    RcTensorMap mAhi[NNETS], mAlo[NNETS];          // A operand as [Bpad, 2H]  (LSTM layers)
-    RcTensorMap mA1hi[NNETS], mA1lo[NNETS];        //              [Bpad, K1p] (linear1)
-    RcTensorMap mA2hi[NNETS], mA2lo[NNETS];        //              [Bpad, H]   (linear2)
+    // split activations (tensor-core path), one set per concurrent lane: [lane][Bpad, 2*Hmax]
+    uint16_t *Ahi[2] = {nullptr, nullptr}, *Alo[2] = {nullptr, nullptr};
+    RcTensorMap mAhi[2][NNETS], mAlo[2][NNETS];    // A operand as [Bpad, 2H]  (LSTM layers)
+    RcTensorMap mA1hi[2][NNETS], mA1lo[2][NNETS];  //              [Bpad, K1p] (linear1)
+    RcTensorMap mA2hi[2][NNETS], mA2lo[2][NNETS];  //              [Bpad, H]   (linear2)
+    // independent sub-net chains (rnn2->rnn3 || rnn4->rnn6, rnn7 || rnn8, late rnn6 || late rnn4) run on two streams
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool tc_ready = false;
     int* flags = nullptr;
     int* lists = nullptr;      // [NLISTS][B]
@@ -329,7 +333,7 @@ int launch_linear(const RcLinear& a, int B, bool lstm, void* stream) {
 }
 
 // one sub-net over the rows of list `li`: X [B, K1] -> (optional) Y
-int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, void* stream) {
+int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, void* stream, int lane = 0) {
     const NetDev& w = s->net->nets[ni];
     NetBuf& nb = s->nb[ni];
     const int B = s->B;
@@ -343,8 +347,8 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
     a.W = w.W1; a.bias = w.b1; a.N = w.H; a.Nw = w.H; a.Y = nb.a1; a.ldy = w.H; a.relu = 1; a.H = w.H;
     const bool tc = s->net->gemm_mode == 1 && s->tc_ready && B > 8;
     if (tc) {
-        RC_TRY(rc_tc_split_rows(X, w.K1, nullptr, 0, w.K1, 0, w.K1p, rows, count, B, s->Ahi, s->Alo, stream));
-        RC_TRY(rc_tc_linear(&s->mA1hi[ni], &s->mA1lo[ni], &w.mW1hi, &w.mW1lo, w.b1, nb.a1, w.H, w.H, w.K1p, 1, rows, count, B, stream));
+        RC_TRY(rc_tc_split_rows(X, w.K1, nullptr, 0, w.K1, 0, w.K1p, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
+        RC_TRY(rc_tc_linear(&s->mA1hi[lane][ni], &s->mA1lo[lane][ni], &w.mW1hi, &w.mW1lo, w.b1, nb.a1, w.H, w.H, w.K1p, 1, rows, count, B, stream));
     } else {
         RC_TRY(launch_linear(a, B, false, stream));
     }
@@ -361,8 +365,8 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
             RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
         }
         if (tc) {
-            RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi, s->Alo, stream));
-            RC_TRY(rc_tc_lstm_layer(&s->mAhi[ni], &s->mAlo[ni], &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
+            RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
+            RC_TRY(rc_tc_lstm_layer(&s->mAhi[lane][ni], &s->mAlo[lane][ni], &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
         } else {
             RC_TRY(launch_linear(a, B, true, stream));
         }
@@ -378,8 +382,8 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
         a.X = nb.hn[1]; a.ldx = w.H; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.H; a.K2 = 0;
         a.W = w.W2; a.bias = w.b2; a.N = w.out; a.Nw = w.out4; a.Y = Y; a.ldy = ldy; a.relu = 0; a.C = nullptr; a.Hout = nullptr;
         if (tc) {
-            RC_TRY(rc_tc_split_rows(nb.hn[1], w.H, nullptr, 0, w.H, 0, w.H, rows, count, B, s->Ahi, s->Alo, stream));
-            RC_TRY(rc_tc_linear(&s->mA2hi[ni], &s->mA2lo[ni], &w.mW2hi, &w.mW2lo, w.b2, Y, ldy, w.out, w.H, 0, rows, count, B, stream));
+            RC_TRY(rc_tc_split_rows(nb.hn[1], w.H, nullptr, 0, w.H, 0, w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
+            RC_TRY(rc_tc_linear(&s->mA2hi[lane][ni], &s->mA2lo[lane][ni], &w.mW2hi, &w.mW2lo, w.b2, Y, ldy, w.out, w.H, 0, rows, count, B, stream));
         } else {
             RC_TRY(launch_linear(a, B, false, stream));
         }
@@ -422,15 +426,26 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
     RC_CHECK_LAUNCH();
     RC_LAUNCH(rc_lists_kernel, 1, NLISTS * 32, 0, stream, s->flags, B, s->lists, s->counts);
     RC_CHECK_LAUNCH();
-    RC_TRY(net_pass(s, NET2, L_ALL, s->X2, s->X3 + 72, RC_K3, stream));                 // j3dr_i            (:144)
-    RC_TRY(net_pass(s, NET3, L_ALL, s->X3, s->Y3, 4, stream));                         // vr                (:145)
-    RC_TRY(net_pass(s, NET4, L_HI, s->X4, s->X6 + 171, RC_K6, stream));                // j3dc              (:153)
-    if (any_first_frame) RC_TRY(net_pass(s, NET6, L_6A, s->X6, s->Y6, 4, stream));     // pc on first_frame (:156)
-    RC_TRY(net_pass(s, NET6, L_6B, s->X6, s->Y6, 4, stream));                          // pc                (:161,165)
+    // fork/join helpers: the side stream runs the chain that is independent of the main one (both inside the same graph when captured)
+    static const bool serial = getenv("RC_SERIAL") != nullptr;               // validation switch: single stream
+    cudaStream_t ms = (cudaStream_t)stream;
+    void* side = serial ? stream : (void*)s->side;
+    const int sl = serial ? 0 : 1;
+    auto fork = [&]() -> int { if (serial) return RC_OK; RC_CUDA(cudaEventRecord(s->ev_fork, ms)); RC_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0)); return RC_OK; };
+    auto join = [&]() -> int { if (serial) return RC_OK; RC_CUDA(cudaEventRecord(s->ev_join, s->side)); RC_CUDA(cudaStreamWaitEvent(ms, s->ev_join, 0)); return RC_OK; };
+    RC_TRY(fork());
+    RC_TRY(net_pass(s, NET2, L_ALL, s->X2, s->X3 + 72, RC_K3, stream, 0));              // j3dr_i            (:144)
+    RC_TRY(net_pass(s, NET3, L_ALL, s->X3, s->Y3, 4, stream, 0));                      // vr                (:145)
+    RC_TRY(net_pass(s, NET4, L_HI, s->X4, s->X6 + 171, RC_K6, side, sl));              // j3dc              (:153)
+    if (any_first_frame) RC_TRY(net_pass(s, NET6, L_6A, s->X6, s->Y6, 4, side, sl));   // pc on first_frame (:156)
+    RC_TRY(net_pass(s, NET6, L_6B, s->X6, s->Y6, 4, side, sl));                        // pc                (:161,165)
+    RC_TRY(join());
     RC_LAUNCH(rc_mid_kernel, rc_cdiv(B, 128), 128, 0, stream, s->flags, B, s->rcr, s->lerpw, s->X3, s->X6, s->X7);
     RC_CHECK_LAUNCH();
-    RC_TRY(net_pass(s, NET7, L_ALL, s->X7, s->Y7, 144, stream));                       // poseg6d           (:169)
-    RC_TRY(net_pass(s, NET8, L_ALL, s->X7, s->Y8, 4, stream));                         // contact logits    (:170)
+    RC_TRY(fork());
+    RC_TRY(net_pass(s, NET7, L_ALL, s->X7, s->Y7, 144, stream, 0));                    // poseg6d           (:169)
+    RC_TRY(net_pass(s, NET8, L_ALL, s->X7, s->Y8, 4, side, sl));                       // contact logits    (:170)
+    RC_TRY(join());
     if (scalar_rows)
         RC_LAUNCH(rc_kin_kernel, rc_cdiv(B, 64), 64, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B, io, s->Y7, s->Y8,
                   s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
@@ -438,9 +453,11 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
         RC_LAUNCH(rc_kin_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B,
                   io, s->Y7, s->Y8, s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
     RC_CHECK_LAUNCH();
+    RC_TRY(fork());
+    RC_TRY(net_pass(s, NET4, L_LATE, s->X4, nullptr, 0, side, sl));                    // vision updater    (:271)
     RC_TRY(init_pass(s, stream));                                                      // (:178-183)
-    RC_TRY(net_pass(s, NET6, L_LATE, s->X6, nullptr, 0, stream));                      // vision updater    (:267)
-    RC_TRY(net_pass(s, NET4, L_LATE, s->X4, nullptr, 0, stream));                      //                   (:271)
+    RC_TRY(net_pass(s, NET6, L_LATE, s->X6, nullptr, 0, stream, 0));                   //                   (:267)
+    RC_TRY(join());
     if (advance) { RC_LAUNCH(rc_advance_kernel, 1, 1, 0, stream, s->d_t); RC_CHECK_LAUNCH(); }
     return RC_OK;
 }
@@ -615,20 +632,26 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
         const long long Bpad = (long long)((B + 127) / 128) * 128;
         int Hmax = 0;
         for (int i = 0; i < NNETS; ++i) Hmax = std::max(Hmax, net->nets[i].H);
-        rc = dev_alloc(s->allocs, &s->Ahi, (size_t)Bpad * 2 * Hmax);
-        if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->Alo, (size_t)Bpad * 2 * Hmax);
-        if (rc == RC_OK) {
-            cudaMemset(s->Ahi, 0, (size_t)Bpad * 2 * Hmax * 2);
-            cudaMemset(s->Alo, 0, (size_t)Bpad * 2 * Hmax * 2);
-            s->tc_ready = true;
+        s->tc_ready = true;
+        for (int ln = 0; ln < 2 && rc == RC_OK; ++ln) {
+            rc = dev_alloc(s->allocs, &s->Ahi[ln], (size_t)Bpad * 2 * Hmax);
+            if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->Alo[ln], (size_t)Bpad * 2 * Hmax);
+            if (rc != RC_OK) break;
+            cudaMemset(s->Ahi[ln], 0, (size_t)Bpad * 2 * Hmax * 2);
+            cudaMemset(s->Alo[ln], 0, (size_t)Bpad * 2 * Hmax * 2);
             for (int i = 0; i < NNETS && s->tc_ready; ++i) {
                 const NetDev& d = net->nets[i];
-                if (rc_tc_make_map(&s->mAhi[i], s->Ahi, Bpad, 2 * d.H, 128) != RC_OK || rc_tc_make_map(&s->mAlo[i], s->Alo, Bpad, 2 * d.H, 128) != RC_OK ||
-                    rc_tc_make_map(&s->mA1hi[i], s->Ahi, Bpad, d.K1p, 128) != RC_OK || rc_tc_make_map(&s->mA1lo[i], s->Alo, Bpad, d.K1p, 128) != RC_OK ||
-                    rc_tc_make_map(&s->mA2hi[i], s->Ahi, Bpad, d.H, 128) != RC_OK || rc_tc_make_map(&s->mA2lo[i], s->Alo, Bpad, d.H, 128) != RC_OK)
+                if (rc_tc_make_map(&s->mAhi[ln][i], s->Ahi[ln], Bpad, 2 * d.H, 128) != RC_OK || rc_tc_make_map(&s->mAlo[ln][i], s->Alo[ln], Bpad, 2 * d.H, 128) != RC_OK ||
+                    rc_tc_make_map(&s->mA1hi[ln][i], s->Ahi[ln], Bpad, d.K1p, 128) != RC_OK || rc_tc_make_map(&s->mA1lo[ln][i], s->Alo[ln], Bpad, d.K1p, 128) != RC_OK ||
+                    rc_tc_make_map(&s->mA2hi[ln][i], s->Ahi[ln], Bpad, d.H, 128) != RC_OK || rc_tc_make_map(&s->mA2lo[ln][i], s->Alo[ln], Bpad, d.H, 128) != RC_OK)
                     s->tc_ready = false;
             }
         }
+    }
+    if (rc == RC_OK) {
+        if (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) { rc_set_error("stream/event creation failed"); rc = RC_ERR_CUDA; }
     }
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->flags, (size_t)B);
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->lists, (size_t)NLISTS * B);
@@ -652,6 +675,9 @@ void rc_state_destroy(rc_state* s) {
     if (s->on_graph) cudaGraphExecDestroy(s->on_graph);
     cudaFree(s->on_din); cudaFree(s->on_dout); cudaFreeHost(s->on_hin); cudaFreeHost(s->on_hout);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    if (s->side) cudaStreamDestroy(s->side);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     for (cudaEvent_t e : s->prof_ev) cudaEventDestroy(e);
     for (void* p : s->allocs) cudaFree(p);
     cudaFree(s->hj); cudaFree(s->ha); cudaFree(s->ho); cudaFree(s->hp); cudaFree(s->ht); cudaFree(s->hft);
@@ -860,8 +886,8 @@ int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* x
     const int* count = s->counts + L_ALL;
     if (mode == 1) {
         if (!(s->tc_ready && B > 8)) { rc_set_error("tensor-core path not available for this state"); return RC_ERR_STATE; }
-        RC_TRY(rc_tc_split_rows(x, w.H, hprev, w.H, w.H, w.H, 2 * w.H, rows, count, B, s->Ahi, s->Alo, stream));
-        RC_TRY(rc_tc_lstm_layer(&s->mAhi[ni], &s->mAlo[ni], &w.mWhi[layer], &w.mWlo[layer], w.bL[layer], c, hout, w.H, rows, count, B, stream));
+        RC_TRY(rc_tc_split_rows(x, w.H, hprev, w.H, w.H, w.H, 2 * w.H, rows, count, B, s->Ahi[0], s->Alo[0], stream));
+        RC_TRY(rc_tc_lstm_layer(&s->mAhi[0][ni], &s->mAlo[0][ni], &w.mWhi[layer], &w.mWlo[layer], w.bL[layer], c, hout, w.H, rows, count, B, stream));
     } else {
         RcLinear a;
         memset(&a, 0, sizeof(a));
