@@ -210,7 +210,11 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     from robustcap_b200 import _lib, synthetic
-    _lib.build()
+    if rank == 0:
+        _lib.build()
+        synthetic.write_assets(synthetic.default_asset_root(), 0)
+    if dist is not None:
+        dist.barrier()
     lib = _lib.load()
     net, sd, assets = build_net()
     B, T = args.seqs, args.frames

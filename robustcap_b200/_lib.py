@@ -51,11 +51,12 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', SO_PATH + '.tmp'] + sources()
+    tmp = '%s.%d.tmp' % (SO_PATH, os.getpid())        # several ranks may build at once: private temp file + atomic rename
+    cmd = [nvcc] + NVCC_FLAGS + ['-o', tmp] + sources()
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)
-    os.replace(SO_PATH + '.tmp', SO_PATH)
+    os.replace(tmp, SO_PATH)
     return SO_PATH
 
 
