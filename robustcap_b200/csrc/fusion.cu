@@ -40,6 +40,7 @@ struct NetDev {
     float *W1 = nullptr, *b1 = nullptr, *WL[2] = {nullptr, nullptr}, *bL[2] = {nullptr, nullptr}, *W2 = nullptr, *b2 = nullptr;
     uint16_t *WLhi[2] = {nullptr, nullptr}, *WLlo[2] = {nullptr, nullptr};   // split-fp16 copies for the tensor-core path
     RcTensorMap mWhi[2], mWlo[2];
+    RcTensorMap mWhi64[2], mWlo64[2];                                        // 64-row boxes for the cluster-multicast kernel
     int K1p = 0, outp = 0;                                                   // linear1 K padded to 64, linear2 rows padded to RC_TC_BN
     uint16_t *W1hi = nullptr, *W1lo = nullptr, *W2hi = nullptr, *W2lo = nullptr;
     RcTensorMap mW1hi, mW1lo, mW2hi, mW2lo;
@@ -75,6 +76,7 @@ struct rc_state {
     // split activations (tensor-core path), one set per concurrent lane: [lane][Bpad, 2*Hmax]
     uint16_t *Ahi[2] = {nullptr, nullptr}, *Alo[2] = {nullptr, nullptr};
     RcTensorMap mAhi[2][NNETS], mAlo[2][NNETS];    // A operand as [Bpad, 2H]  (LSTM layers)
+    RcTensorMap mAhi64[2][NNETS], mAlo64[2][NNETS];  // same with 64-row boxes (cluster-multicast kernel)
     RcTensorMap mA1hi[2][NNETS], mA1lo[2][NNETS];  //              [Bpad, K1p] (linear1)
     RcTensorMap mA2hi[2][NNETS], mA2lo[2][NNETS];  //              [Bpad, H]   (linear2)
     // independent sub-net chains (rnn2->rnn3 || rnn4->rnn6, rnn7 || rnn8, late rnn6 || late rnn4) run on two streams
@@ -366,7 +368,11 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
         }
         if (tc) {
             RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
-            RC_TRY(rc_tc_lstm_layer(&s->mAhi[lane][ni], &s->mAlo[lane][ni], &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
+            static const bool use_cluster = getenv("RC_TC_NOCLUSTER") == nullptr;     // tuning / validation switch
+            if (use_cluster && B > 128)
+                RC_TRY(rc_tc_lstm_layer_cluster(&s->mAhi64[lane][ni], &s->mAlo64[lane][ni], &w.mWhi64[l], &w.mWlo64[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
+            else
+                RC_TRY(rc_tc_lstm_layer(&s->mAhi[lane][ni], &s->mAlo[lane][ni], &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
         } else {
             RC_TRY(launch_linear(a, B, true, stream));
         }
@@ -583,7 +589,9 @@ int rc_net_finalize(rc_net* n) {
         n->tc_ready = true;
         for (int l = 0; l < 2 && n->tc_ready; ++l) {
             if (rc_tc_make_map(&d.mWhi[l], d.WLhi[l], 4LL * d.H, 2 * d.H, RC_TC_BN) != RC_OK ||
-                rc_tc_make_map(&d.mWlo[l], d.WLlo[l], 4LL * d.H, 2 * d.H, RC_TC_BN) != RC_OK) n->tc_ready = false;
+                rc_tc_make_map(&d.mWlo[l], d.WLlo[l], 4LL * d.H, 2 * d.H, RC_TC_BN) != RC_OK ||
+                rc_tc_make_map(&d.mWhi64[l], d.WLhi[l], 4LL * d.H, 2 * d.H, 64) != RC_OK ||
+                rc_tc_make_map(&d.mWlo64[l], d.WLlo[l], 4LL * d.H, 2 * d.H, 64) != RC_OK) n->tc_ready = false;
         }
         RC_TRY(pack_linear(n, p + ".linear2", d.out, d.H, d.out4, d.H, &d.W2, &d.b2, d.outp, d.H, &d.W2hi, &d.W2lo));
         if (n->tc_ready) {
@@ -641,7 +649,8 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
             cudaMemset(s->Alo[ln], 0, (size_t)Bpad * 2 * Hmax * 2);
             for (int i = 0; i < NNETS && s->tc_ready; ++i) {
                 const NetDev& d = net->nets[i];
-                if (rc_tc_make_map(&s->mAhi[ln][i], s->Ahi[ln], Bpad, 2 * d.H, 128) != RC_OK || rc_tc_make_map(&s->mAlo[ln][i], s->Alo[ln], Bpad, 2 * d.H, 128) != RC_OK ||
+                if (rc_tc_make_map(&s->mAhi64[ln][i], s->Ahi[ln], Bpad, 2 * d.H, 64) != RC_OK || rc_tc_make_map(&s->mAlo64[ln][i], s->Alo[ln], Bpad, 2 * d.H, 64) != RC_OK ||
+                    rc_tc_make_map(&s->mAhi[ln][i], s->Ahi[ln], Bpad, 2 * d.H, 128) != RC_OK || rc_tc_make_map(&s->mAlo[ln][i], s->Alo[ln], Bpad, 2 * d.H, 128) != RC_OK ||
                     rc_tc_make_map(&s->mA1hi[ln][i], s->Ahi[ln], Bpad, d.K1p, 128) != RC_OK || rc_tc_make_map(&s->mA1lo[ln][i], s->Alo[ln], Bpad, d.K1p, 128) != RC_OK ||
                     rc_tc_make_map(&s->mA2hi[ln][i], s->Ahi[ln], Bpad, d.H, 128) != RC_OK || rc_tc_make_map(&s->mA2lo[ln][i], s->Alo[ln], Bpad, d.H, 128) != RC_OK)
                     s->tc_ready = false;

@@ -61,6 +61,21 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                  ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -260,6 +275,164 @@ rc_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ 
     }
 }
 
+// 2 x 2 thread-block-cluster variant of the fused LSTM layer: the four CTAs of a cluster cover 2 N-tiles x 2 M-tiles; every
+// operand tile is fetched from L2 once per cluster (each CTA loads a 64-row half of its A tile and of its W tile and TMA-
+// multicasts it to the CTA that shares that tile), halving the L2->SM operand traffic that bounds the single-CTA kernel.
+// Protocol: full[s] expects the whole 64 KB stage (halves arrive from two CTAs); empty[s] counts 3 arrivals — the
+// tcgen05.commit of this CTA, of its row peer and of its column peer (multicast commit) — because those are the CTAs whose
+// smem this CTA's producer overwrites; cluster-wide barriers fence start and exit.
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 2, 1) __launch_bounds__(kTcThreads, 1)
+rc_tc_lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+             const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, TcArgs a) {
+    constexpr int A_BYTES = kTcBM * kTcBK * 2;     // 16 KB
+    constexpr int W_BYTES = BN * kTcBK * 2;
+    constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+    constexpr int TM_COLS = 4 * BN;                // 3 x main + corr
+    static_assert(TM_COLS == 512 || TM_COLS == 256, "TMEM allocation must be a power of two");
+    constexpr bool LSTM = true;
+    static_assert(BN == 128, "half tiles are 64 rows");
+    const int cnt = *a.count;
+    const int m0 = blockIdx.y * kTcBM;
+    if ((int)(blockIdx.y & ~1u) * kTcBM >= cnt) return;          // uniform over the cluster: both M tiles are empty
+    const int n0 = blockIdx.x * BN;
+    const uint32_t cx = blockIdx.x & 1u, cy = blockIdx.y & 1u;     // position inside the 2 x 2 cluster
+    const uint32_t crank = cluster_ctarank();                      // == cx + 2 * cy (x fastest)
+    const uint16_t row_mask = (uint16_t)(3u << (cy * 2));          // CTAs sharing this A tile (same M tile)
+    const uint16_t col_mask = (uint16_t)(5u << cx);                // CTAs sharing this W tile (same N tile)
+    const uint16_t commit_mask = (uint16_t)((1u << crank) | (1u << (crank ^ 1u)) | (1u << (crank ^ 2u)));
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[STAGES];
+    __shared__ __align__(8) uint64_t bar_empty[STAGES];
+    __shared__ __align__(8) uint64_t bar_acc;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = a.K / kTcBK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 3); }
+        mbar_init(smem_u32(&bar_acc), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(TM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                            // every CTA's barriers exist before any multicast targets them
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
+                const uint32_t full = smem_u32(&bar_full[s]);
+                mbar_expect_tx(full, STAGE_BYTES);
+                const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                // 64-row halves (8 KB each): A half `cx` to the row peers, W half `cy` to the column peers
+                tma_load_2d_mc(base + cx * (A_BYTES / 2), &tmAhi, kb * kTcBK, m0 + (int)cx * 64, full, row_mask);
+                tma_load_2d_mc(base + A_BYTES + cx * (A_BYTES / 2), &tmAlo, kb * kTcBK, m0 + (int)cx * 64, full, row_mask);
+                tma_load_2d_mc(base + 2 * A_BYTES + cy * (W_BYTES / 2), &tmWhi, kb * kTcBK, n0 + (int)cy * 64, full, col_mask);
+                tma_load_2d_mc(base + 2 * A_BYTES + W_BYTES + cy * (W_BYTES / 2), &tmWlo, kb * kTcBK, n0 + (int)cy * 64, full, col_mask);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor (cute UMMA::InstrDescriptor): c_format F32 = 1 at [4,6); a/b format F16 = 0; K-major both;
+            // n_dim = N >> 3 at [17,23); m_dim = M >> 4 at [24,29)
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+            const uint32_t d_corr = tmem_base + 3 * BN;
+            int g = 0;                                           // global K-step counter
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(smem_u32(&bar_full[s]), ph);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                const uint64_t dAhi = make_desc(base), dAlo = make_desc(base + A_BYTES);
+                const uint64_t dWhi = make_desc(base + 2 * A_BYTES), dWlo = make_desc(base + 2 * A_BYTES + W_BYTES);
+#pragma unroll
+                for (int k = 0; k < kTcBK / 16; ++k, ++g) {
+                    const uint64_t adv = (uint64_t)(k * 2);      // 16 fp16 = 32 bytes = 2 x 16-byte units
+                    const uint32_t d_main = tmem_base + (uint32_t)((g % 3) * BN);
+                    tc_mma_f16(d_main, dAhi + adv, dWhi + adv, idesc, g >= 3 ? 1u : 0u);
+                    tc_mma_f16(d_corr, dAhi + adv, dWlo + adv, idesc, g ? 1u : 0u);
+                    tc_mma_f16(d_corr, dAlo + adv, dWhi + adv, idesc, 1u);
+                }
+                tc_commit_mc(smem_u32(&bar_empty[s]), commit_mask);  // frees the stage here and in the two CTAs that write into it
+            }
+            tc_commit(smem_u32(&bar_acc));                       // accumulators complete
+        }
+    } else {
+        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
+        mbar_wait(smem_u32(&bar_acc), 0);
+        tc_fence_after();
+        const int mrow = m0 + q * 32 + lane;
+        const int row = (mrow < cnt) ? a.rows[mrow] : -1;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int nmain = (KB * (kTcBK / 16) >= 3) ? 3 : KB * (kTcBK / 16);   // accumulators that were written
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v0[32], v1[32];
+            float acc[32];
+            tc_ld32(lane_base + (uint32_t)(c * 32), v0);
+            tc_ld32(lane_base + (uint32_t)(3 * BN + c * 32), v1);
+            tc_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v0[e]);
+            if (nmain > 1) {
+                tc_ld32(lane_base + (uint32_t)(BN + c * 32), v0);
+                tc_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
+            }
+            if (nmain > 2) {
+                tc_ld32(lane_base + (uint32_t)(2 * BN + c * 32), v0);
+                tc_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] = fmaf(__uint_as_float(v1[e]), 4.8828125e-4f, acc[e]);    // + corr * 2^-11
+            if (row >= 0) {
+                if (LSTM) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int n = n0 + c * 32 + u * 4;
+                        const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
+                        const size_t idx = (size_t)row * a.H + (n >> 2);
+                        const float cn = fmaf(sigm(acc[u * 4 + 1] + b.y), a.C[idx], sigm(acc[u * 4 + 0] + b.x) * tanhf(acc[u * 4 + 2] + b.z));
+                        a.C[idx] = cn;
+                        a.Hout[idx] = sigm(acc[u * 4 + 3] + b.w) * tanhf(cn);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) {
+                        const int n = n0 + c * 32 + e;
+                        if (n < a.N) {
+                            float y = acc[e] + a.bias[n];
+                            if (a.relu) y = fmaxf(y, 0.f);
+                            a.Y[(size_t)row * a.ldy + n] = y;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();                                            // no CTA leaves while a peer can still write its smem / barriers
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TM_COLS) : "memory");
+    }
+}
+
 // Gather the rows of a list from the two K segments, split every fp32 into (hi, lo) fp16 halves, write dense [*, K] rows.
 __global__ void __launch_bounds__(256) rc_split_rows_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ X2, int ldx2,
                                                              int K1, int K2, int Kout, const int* __restrict__ rows,
@@ -363,6 +536,27 @@ static int tc_stages() {
         stages = (e && atoi(e) == 2) ? 2 : 3;
     }
     return stages;
+}
+
+int rc_tc_lstm_layer_cluster(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                             const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream) {
+    // tensor maps here have 64-row boxes (half tiles)
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
+    constexpr int BN = RC_TC_BN, STAGES = 3;
+    constexpr int SMEM = STAGES * (2 * kTcBM * kTcBK * 2 + 2 * BN * kTcBK * 2) + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        RC_CUDA(cudaFuncSetAttribute(rc_tc_lstm_cluster_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        attr_set = true;
+    }
+    const int mt = rc_cdiv(B, kTcBM);
+    dim3 grid(4 * H / BN, (mt + 1) / 2 * 2);            // both grid dimensions are multiples of the 2 x 2 cluster
+    RC_LAUNCH((rc_tc_lstm_cluster_kernel<BN, STAGES>), grid, kTcThreads, SMEM, stream, *(const CUtensorMap*)mAhi, *(const CUtensorMap*)mAlo,
+              *(const CUtensorMap*)mWhi, *(const CUtensorMap*)mWlo, a);
+    RC_CHECK_LAUNCH();
+    return RC_OK;
 }
 
 int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,

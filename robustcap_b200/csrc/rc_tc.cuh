@@ -18,6 +18,9 @@ int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1,
 // plain linear layer Y = act(A W^T + b) on the tensor cores (W rows padded to a multiple of RC_TC_BN, K to 64)
 int rc_tc_linear(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
                  const float* bias, float* Y, int ldy, int N, int K, int relu, const int* rows, const int* count, int B, void* stream);
+// same on 2 x 2 thread-block clusters with TMA multicast; the four tensor maps must have 64-row boxes
+int rc_tc_lstm_layer_cluster(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
+                             const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream);
 // fused LSTM layer on the tensor cores over the rows of a list
 int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
                      const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream);
