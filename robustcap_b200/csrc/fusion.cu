@@ -368,7 +368,7 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
         }
         if (tc) {
             RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
-            static const bool use_cluster = getenv("RC_TC_NOCLUSTER") == nullptr;     // tuning / validation switch
+            static const bool use_cluster = getenv("RC_TC_CLUSTER") != nullptr;      // experiment switch (measured slower)
             if (use_cluster && B > 128)
                 RC_TRY(rc_tc_lstm_layer_cluster(&s->mAhi64[lane][ni], &s->mAlo64[lane][ni], &w.mWhi64[l], &w.mWlo64[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
             else

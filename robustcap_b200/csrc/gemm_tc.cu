@@ -125,6 +125,7 @@ struct TcArgs {
     const int* rows;       // row list (stream indices); compact row i of the A operand belongs to stream rows[i]
     const int* count;
     int H, K;
+    int dbg;               // timing experiments only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
 };
 
 // TMEM plan (512 columns): three "main" accumulators used round-robin over the K steps + one "corr" accumulator.
@@ -177,6 +178,7 @@ rc_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ 
                 const uint32_t ph = (kb / STAGES) & 1;
                 mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1);
                 const uint32_t full = smem_u32(&bar_full[s]);
+                if (a.dbg == 2) { mbar_expect_tx(full, 0); continue; }
                 mbar_expect_tx(full, STAGE_BYTES);
                 const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
                 tma_load_2d(base, &tmAhi, kb * kTcBK, m0, full);
@@ -202,6 +204,7 @@ rc_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ 
                 const uint64_t dWhi = make_desc(base + 2 * A_BYTES), dWlo = make_desc(base + 2 * A_BYTES + W_BYTES);
 #pragma unroll
                 for (int k = 0; k < kTcBK / 16; ++k, ++g) {
+                    if (a.dbg == 1) continue;
                     const uint64_t adv = (uint64_t)(k * 2);      // 16 fp16 = 32 bytes = 2 x 16-byte units
                     const uint32_t d_main = tmem_base + (uint32_t)((g % 3) * BN);
                     tc_mma_f16(d_main, dAhi + adv, dWhi + adv, idesc, g >= 3 ? 1u : 0u);
@@ -564,6 +567,9 @@ int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcT
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("RC_TC_DBG"); dbg = e ? atoi(e) : 0; }
+    a.dbg = dbg;
     if (tc_stages() == 2) return launch_tc<RC_TC_BN, 2, true>(mAhi, mAlo, mWhi, mWlo, a, 4 * H, B, stream);
     return launch_tc<RC_TC_BN, 3, true>(mAhi, mAlo, mWhi, mWlo, a, 4 * H, B, stream);
 }
