@@ -29,7 +29,7 @@ namespace {
 
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 64;          // fp16 elements = 128 bytes
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;     // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -128,6 +128,98 @@ struct TcArgs {
     int dbg;               // timing experiments only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
 };
 
+// Epilogue shared by the tcgen05 kernels: 8 warps (2 per TMEM lane quarter, each taking half of the BN columns).  Thread =
+// one output row.  The cell state of the row is prefetched with 128-bit loads BEFORE the accumulators are waited for (the
+// epilogue warps idle during the main loop), and c / h leave as 128-bit stores: a row's 8 units are one full 32-byte sector,
+// instead of 32 scattered 4-byte accesses per warp instruction with the dependent-load latency exposed per unit (measured:
+// the old per-unit load-compute-store loop made the kernel time insensitive to removing every MMA or every TMA load).
+template <int BN, bool LSTM>
+__device__ __forceinline__ void tc_epilogue(const TcArgs& a, uint32_t tmem_base, uint32_t bar_acc_addr, int m0, int n0, int cnt,
+                                            int ewarp, int lane, int nmain) {
+    constexpr int CH = BN / 32;                 // 32-column chunks in the tile
+    constexpr int CPW = CH / 2;                 // chunks per warp
+    const int q = (ewarp + 2) & 3, half = ewarp >> 2;   // a warp may only read TMEM lanes 32 * (warp_id % 4) ..; ewarp = warp_id - 2
+    const int mrow = m0 + q * 32 + lane;
+    const int row = (mrow < cnt) ? a.rows[mrow] : -1;
+    float4 cprev[CPW][2];
+    if (LSTM && row >= 0) {
+#pragma unroll
+        for (int cc = 0; cc < CPW; ++cc) {
+            const float* cp = a.C + (size_t)row * a.H + ((n0 + (half * CPW + cc) * 32) >> 2);
+            cprev[cc][0] = *reinterpret_cast<const float4*>(cp);
+            cprev[cc][1] = *reinterpret_cast<const float4*>(cp + 4);
+        }
+    }
+    mbar_wait(bar_acc_addr, 0);
+    tc_fence_after();
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+    for (int cc = 0; cc < CPW; ++cc) {
+        const int c = half * CPW + cc;
+        uint32_t v0[32], v1[32];
+        float acc[32];
+        tc_ld32(lane_base + (uint32_t)(c * 32), v0);
+        tc_ld32(lane_base + (uint32_t)(3 * BN + c * 32), v1);
+        tc_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v0[e]);
+        if (nmain > 1) {
+            tc_ld32(lane_base + (uint32_t)(BN + c * 32), v0);
+            tc_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
+        }
+        if (nmain > 2) {
+            tc_ld32(lane_base + (uint32_t)(2 * BN + c * 32), v0);
+            tc_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = fmaf(__uint_as_float(v1[e]), 4.8828125e-4f, acc[e]);    // + corr * 2^-11
+        if (row < 0) continue;
+        const int nb = n0 + c * 32;
+        if (LSTM) {
+            const float cp[8] = {cprev[cc][0].x, cprev[cc][0].y, cprev[cc][0].z, cprev[cc][0].w,
+                                 cprev[cc][1].x, cprev[cc][1].y, cprev[cc][1].z, cprev[cc][1].w};
+            float cn[8], hn[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + nb + u * 4));
+                cn[u] = fmaf(sigm(acc[u * 4 + 1] + b.y), cp[u], sigm(acc[u * 4 + 0] + b.x) * tanhf(acc[u * 4 + 2] + b.z));
+                hn[u] = sigm(acc[u * 4 + 3] + b.w) * tanhf(cn[u]);
+            }
+            const size_t idx = (size_t)row * a.H + (nb >> 2);
+            *reinterpret_cast<float4*>(a.C + idx) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+            *reinterpret_cast<float4*>(a.C + idx + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+            *reinterpret_cast<float4*>(a.Hout + idx) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+            *reinterpret_cast<float4*>(a.Hout + idx + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+        } else {
+            float* yrow = a.Y + (size_t)row * a.ldy;
+            const bool vec = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && (nb + 32 <= a.N);
+            if (vec) {
+#pragma unroll
+                for (int e = 0; e < 32; e += 4) {
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + nb + e));
+                    float4 y = make_float4(acc[e] + b.x, acc[e + 1] + b.y, acc[e + 2] + b.z, acc[e + 3] + b.w);
+                    if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+                    *reinterpret_cast<float4*>(yrow + nb + e) = y;
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) {
+                    const int n = nb + e;
+                    if (n < a.N) {
+                        float y = acc[e] + a.bias[n];
+                        if (a.relu) y = fmaxf(y, 0.f);
+                        yrow[n] = y;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // TMEM plan (512 columns): three "main" accumulators used round-robin over the K steps + one "corr" accumulator.
 // The tensor core adds into the fp32 accumulator with truncation, a drift that grows with the number of MMAs chained on
 // one accumulator (measured: 3.6x the rms error of sequential fp32 FMAs at K = 2560); three independent chains cut it 3x
@@ -216,60 +308,8 @@ rc_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ 
             tc_commit(smem_u32(&bar_acc));                       // accumulators complete
         }
     } else {
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-        mbar_wait(smem_u32(&bar_acc), 0);
-        tc_fence_after();
-        const int mrow = m0 + q * 32 + lane;
-        const int row = (mrow < cnt) ? a.rows[mrow] : -1;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const int nmain = (KB * (kTcBK / 16) >= 3) ? 3 : KB * (kTcBK / 16);   // accumulators that were written
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v0[32], v1[32];
-            float acc[32];
-            tc_ld32(lane_base + (uint32_t)(c * 32), v0);
-            tc_ld32(lane_base + (uint32_t)(3 * BN + c * 32), v1);
-            tc_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v0[e]);
-            if (nmain > 1) {
-                tc_ld32(lane_base + (uint32_t)(BN + c * 32), v0);
-                tc_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
-            }
-            if (nmain > 2) {
-                tc_ld32(lane_base + (uint32_t)(2 * BN + c * 32), v0);
-                tc_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 32; ++e) acc[e] = fmaf(__uint_as_float(v1[e]), 4.8828125e-4f, acc[e]);    // + corr * 2^-11
-            if (row >= 0) {
-                if (LSTM) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int n = n0 + c * 32 + u * 4;
-                        const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
-                        const size_t idx = (size_t)row * a.H + (n >> 2);
-                        const float cn = fmaf(sigm(acc[u * 4 + 1] + b.y), a.C[idx], sigm(acc[u * 4 + 0] + b.x) * tanhf(acc[u * 4 + 2] + b.z));
-                        a.C[idx] = cn;
-                        a.Hout[idx] = sigm(acc[u * 4 + 3] + b.w) * tanhf(cn);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int n = n0 + c * 32 + e;
-                        if (n < a.N) {
-                            float y = acc[e] + a.bias[n];
-                            if (a.relu) y = fmaxf(y, 0.f);
-                            a.Y[(size_t)row * a.ldy + n] = y;
-                        }
-                    }
-                }
-            }
-        }
+        tc_epilogue<BN, LSTM>(a, tmem_base, smem_u32(&bar_acc), m0, n0, cnt, warp - 2, lane, nmain);
     }
     tc_fence_before();
     __syncthreads();
@@ -374,60 +414,8 @@ rc_tc_lstm_cluster_kernel(const __grid_constant__ CUtensorMap tmAhi, const __gri
             tc_commit(smem_u32(&bar_acc));                       // accumulators complete
         }
     } else {
-        const int q = warp & 3;                                  // TMEM lane quarter this warp may read
-        mbar_wait(smem_u32(&bar_acc), 0);
-        tc_fence_after();
-        const int mrow = m0 + q * 32 + lane;
-        const int row = (mrow < cnt) ? a.rows[mrow] : -1;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         const int nmain = (KB * (kTcBK / 16) >= 3) ? 3 : KB * (kTcBK / 16);   // accumulators that were written
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v0[32], v1[32];
-            float acc[32];
-            tc_ld32(lane_base + (uint32_t)(c * 32), v0);
-            tc_ld32(lane_base + (uint32_t)(3 * BN + c * 32), v1);
-            tc_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) acc[e] = __uint_as_float(v0[e]);
-            if (nmain > 1) {
-                tc_ld32(lane_base + (uint32_t)(BN + c * 32), v0);
-                tc_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
-            }
-            if (nmain > 2) {
-                tc_ld32(lane_base + (uint32_t)(2 * BN + c * 32), v0);
-                tc_ld_wait();
-#pragma unroll
-                for (int e = 0; e < 32; ++e) acc[e] += __uint_as_float(v0[e]);
-            }
-#pragma unroll
-            for (int e = 0; e < 32; ++e) acc[e] = fmaf(__uint_as_float(v1[e]), 4.8828125e-4f, acc[e]);    // + corr * 2^-11
-            if (row >= 0) {
-                if (LSTM) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int n = n0 + c * 32 + u * 4;
-                        const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
-                        const size_t idx = (size_t)row * a.H + (n >> 2);
-                        const float cn = fmaf(sigm(acc[u * 4 + 1] + b.y), a.C[idx], sigm(acc[u * 4 + 0] + b.x) * tanhf(acc[u * 4 + 2] + b.z));
-                        a.C[idx] = cn;
-                        a.Hout[idx] = sigm(acc[u * 4 + 3] + b.w) * tanhf(cn);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) {
-                        const int n = n0 + c * 32 + e;
-                        if (n < a.N) {
-                            float y = acc[e] + a.bias[n];
-                            if (a.relu) y = fmaxf(y, 0.f);
-                            a.Y[(size_t)row * a.ldy + n] = y;
-                        }
-                    }
-                }
-            }
-        }
+        tc_epilogue<BN, LSTM>(a, tmem_base, smem_u32(&bar_acc), m0, n0, cnt, warp - 2, lane, nmain);
     }
     tc_fence_before();
     cluster_sync_all();                                            // no CTA leaves while a peer can still write its smem / barriers
