@@ -106,6 +106,15 @@ class ClockSampler:
         return out
 
 
+def dominant_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/r01_tc_traffic.json, written from the .ncu-rep by profiles/extract_traffic.py); None when absent."""
+    path = os.path.join(REPO, 'profiles', 'r01_tc_traffic.json')
+    if os.path.exists(path):
+        return json.load(open(path)).get('dram_bytes_per_launch')
+    return None
+
+
 def build_net(seed=0):
     from robustcap_b200 import synthetic, Net, ParametricModel
     assets = synthetic.write_assets(synthetic.default_asset_root(), 0)
@@ -305,7 +314,7 @@ def main():
                           '3 MMAs per fp32-accurate product; the event pair also covers the row-gather/split pre-pass)', 'bound': 'tensor',
                 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': dom_tflops / pk['tflops_sustained'], 'peak_source': 'bf16 sustained, of ' + pk['source'],
-                'traffic': None, 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,
+                'traffic': dominant_traffic(), 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,
                 'whole_path_tflops': FLOP_PER_FRAME * B * T / (ms_step * 1e-3) / 1e12,
                 'weight_stream_gbs': WEIGHT_BYTES * T / (ms_step * 1e-3) / 1e9}
     line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
