@@ -21,107 +21,10 @@
 #include "rc_linear.cuh"
 #include "rc_pack.h"
 #include "rc_tc.cuh"
+#include "rc_fusion.cuh"
 
 namespace {
 
-enum { NET2 = 0, NET3, NET4, NET6, NET7, NET8, NNETS };
-const int kNetId[NNETS] = {2, 3, 4, 6, 7, 8};
-const int kNetIn[NNETS] = {72, 141, 171, 240, 141, 141};
-const int kNetK1[NNETS] = {RC_K2, RC_K3, RC_K4, RC_K6, RC_K7, RC_K7};
-const int kNetH[NNETS] = {512, 512, 1280, 1024, 512, 512};
-const int kNetOut[NNETS] = {69, 3, 69, 3, 144, 2};
-const int kInitDims[4] = {69, 512, 1024, 2048};
-constexpr int kInitK0 = 80;
-
-enum { L_ALL = 0, L_HI, L_6A, L_6B, L_LATE, L_INIT, NLISTS };
-
-struct NetDev {
-    int in = 0, K1 = 0, H = 0, out = 0, out4 = 0;
-    float *W1 = nullptr, *b1 = nullptr, *WL[2] = {nullptr, nullptr}, *bL[2] = {nullptr, nullptr}, *W2 = nullptr, *b2 = nullptr;
-    uint16_t *WLhi[2] = {nullptr, nullptr}, *WLlo[2] = {nullptr, nullptr};   // split-fp16 copies for the tensor-core path
-    RcTensorMap mWhi[2], mWlo[2];
-    RcTensorMap mWhi64[2], mWlo64[2];                                        // 64-row boxes for the cluster-multicast kernel
-    int K1p = 0, outp = 0;                                                   // linear1 K padded to 64, linear2 rows padded to RC_TC_BN
-    uint16_t *W1hi = nullptr, *W1lo = nullptr, *W2hi = nullptr, *W2lo = nullptr;
-    RcTensorMap mW1hi, mW1lo, mW2hi, mW2lo;
-};
-struct NetBuf {
-    float *h[2] = {nullptr, nullptr}, *c[2] = {nullptr, nullptr}, *hn[2] = {nullptr, nullptr}, *a1 = nullptr;
-};
-
-}  // namespace
-
-struct rc_net {
-    const rc_model* model = nullptr;
-    RcNetCfg cfg;
-    std::map<std::string, std::vector<float>> staging;
-    bool finalized = false;
-    NetDev nets[NNETS];
-    float *Wi[3] = {nullptr, nullptr, nullptr}, *bi[3] = {nullptr, nullptr, nullptr};   // init_net
-    int64_t weight_bytes = 0;
-    std::vector<void*> allocs;
-    int gemm_mode = 1;          // 0 = fp32 SIMT tiles, 1 = tcgen05 split-fp16 (batches > 8 streams)
-    bool tc_ready = false;
-};
-
-struct rc_state {
-    const rc_net* net = nullptr;
-    int B = 0;
-    std::vector<void*> allocs;
-    NetBuf nb[NNETS];
-    float *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *X6 = nullptr, *X7 = nullptr, *XI = nullptr;
-    float *Y3 = nullptr, *Y6 = nullptr, *Y7 = nullptr, *Y8 = nullptr, *Ydump = nullptr;
-    float *I1 = nullptr, *I2 = nullptr, *I3 = nullptr;
-    float *rcr = nullptr, *conf = nullptr, *lerpw = nullptr, *gravity = nullptr;
-    // split activations (tensor-core path), one set per concurrent lane: [lane][Bpad, 2*Hmax]
-    uint16_t *Ahi[2] = {nullptr, nullptr}, *Alo[2] = {nullptr, nullptr};
-    RcTensorMap mAhi[2][NNETS], mAlo[2][NNETS];    // A operand as [Bpad, 2H]  (LSTM layers)
-    RcTensorMap mAhi64[2][NNETS], mAlo64[2][NNETS];  // same with 64-row boxes (cluster-multicast kernel)
-    RcTensorMap mA1hi[2][NNETS], mA1lo[2][NNETS];  //              [Bpad, K1p] (linear1)
-    RcTensorMap mA2hi[2][NNETS], mA2lo[2][NNETS];  //              [Bpad, H]   (linear2)
-    // independent sub-net chains (rnn2->rnn3 || rnn4->rnn6, rnn7 || rnn8, late rnn6 || late rnn4) run on two streams
-    cudaStream_t side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    bool tc_ready = false;
-    int* flags = nullptr;
-    int* lists = nullptr;      // [NLISTS][B]
-    int* counts = nullptr;     // [NLISTS]
-    int* d_t = nullptr;        // device frame cursor (sequence mode)
-    RcRowState* rows = nullptr;
-    // cached CUDA graph of one steady-state frame
-    cudaGraphExec_t graph = nullptr;
-    std::vector<const void*> graph_key;
-    cudaStream_t cap_stream = nullptr;   // capture happens here (the legacy default stream cannot be captured)
-    long long graph_nodes = 0;           // kernel nodes in the captured frame (launch accounting)
-    // optional CUDA-event timing of the dominant kernel (rnn4's fused LSTM layers), see rc_profile_*
-    int prof_on = 0;
-    std::vector<cudaEvent_t> prof_ev;
-    size_t prof_used = 0;
-    // low-latency single-frame path (rc_forward_online): fixed staging buffers so the frame is one cached CUDA graph
-    float *on_din = nullptr, *on_dout = nullptr, *on_hin = nullptr, *on_hout = nullptr;   // device / pinned host
-    cudaGraphExec_t on_graph = nullptr;
-    void* on_graph_stream = nullptr;
-    long long on_graph_nodes = 0;
-    // staging buffers of rc_forward_sequence_host
-    float *hj = nullptr, *ha = nullptr, *ho = nullptr, *hp = nullptr, *ht = nullptr, *hft = nullptr;
-    int *hlen = nullptr, *hfl = nullptr;
-    int64_t host_cap_T = 0;
-};
-
-namespace {
-
-struct StepIO {
-    const float *j2dc, *accc, *oric;       // bases
-    long long sj, sa, so;                  // per-stream strides (floats)
-    const float* gravity;                  // [B,3] or nullptr
-    const float* first_tran;               // [B,3] or nullptr
-    const int* row_flags;                  // [B] or nullptr
-    const int* lengths;                    // [B] or nullptr
-    float *pose, *tran;                    // bases
-    long long sp, st;                      // per-stream strides
-    const int* d_t;                        // frame cursor or nullptr (t = 0)
-    int first_mode;                        // 0 never, 1 always, 2 only at t == 0
-};
 
 __global__ void __launch_bounds__(128) rc_prep_kernel(RcNetCfg cfg, const RcRowState* __restrict__ rows, StepIO io, int B,
                                                        float* X2, float* X3, float* X4, float* X6, float* X7,
@@ -312,9 +215,7 @@ int launch_linear(const RcLinear& a, int B, bool lstm, void* stream) {
     if (B <= 8) {
         const int njobs = a.Nw / 4;
         const int K = a.K1 + a.K2;
-        // enough warps to cover the SMs twice, but never split a K shorter than one warp pass
-        int ksplit = 1;
-        while (ksplit < 8 && njobs * ksplit < 2 * 148 * 8 && K / (ksplit * 2) >= 128) ksplit *= 2;
+        const int ksplit = rc_gemv_ksplit(K);
         const int jpb = 8 / ksplit;
         const int grid = rc_cdiv(njobs, jpb);
 #define RC_GEMV(MM)                                                                          \
@@ -682,6 +583,7 @@ void rc_state_destroy(rc_state* s) {
     if (!s) return;
     if (s->graph) cudaGraphExecDestroy(s->graph);
     if (s->on_graph) cudaGraphExecDestroy(s->on_graph);
+    cudaFree(s->sk_bar); cudaFree(s->sk_rows);
     cudaFree(s->on_din); cudaFree(s->on_dout); cudaFreeHost(s->on_hin); cudaFreeHost(s->on_hout);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     if (s->side) cudaStreamDestroy(s->side);
@@ -767,7 +669,9 @@ int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const f
     io.j2dc = s->on_din; io.accc = s->on_din + 99; io.oric = s->on_din + 117; io.sj = 99; io.sa = 18; io.so = 54;
     io.gravity = nullptr; io.first_tran = s->on_din + 171; io.row_flags = (const int*)(s->on_din + 174); io.lengths = nullptr;
     io.pose = s->on_dout; io.tran = s->on_dout + 216; io.sp = 216; io.st = 3; io.d_t = nullptr; io.first_mode = 1;
-    if (first_frame) {
+    if (rc_stream_supported(s)) {
+        RC_TRY(rc_stream_frame(s, io, first_frame, stream));    // the whole frame as one cooperative kernel (stream.cu)
+    } else if (first_frame) {
         RC_TRY(enqueue_step(s, io, 1, false, stream));          // extra rnn6 pass (sig_mp.py:155-156): direct launches
     } else {
         if (!s->on_graph || s->on_graph_stream != stream) {

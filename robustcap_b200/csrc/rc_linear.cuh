@@ -49,14 +49,16 @@ __device__ __forceinline__ void rc_lstm_cell(float pi, float pf, float pg, float
 // ---------------------------------------------------------------------------------------------------------------
 // GEMV path: up to M streams.  Block = 8 warps; `ksplit` warps share one job (= 4 consecutive weight rows = one
 // hidden unit for the LSTM layers) by splitting K.
-template <int M, bool LSTM>
-__global__ void __launch_bounds__(256) rc_gemv_kernel(RcLinear a, int ksplit) {
-    __shared__ float part[8][4 * M];
-    const int cnt = min(*a.count, M);
-    if (cnt == 0) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// K-split policy shared by the GEMV launches and the single-stream cooperative kernel (identical arithmetic in both).
+__host__ __device__ __forceinline__ int rc_gemv_ksplit(int K) { return K >= 1024 ? 8 : (K >= 512 ? 4 : 1); }
+
+// One "virtual block" (8 warps, `warp` in 0..7) of the GEMV: jobs [vb * jpb, (vb + 1) * jpb).  `part` is 8 x 4M floats of shared
+// memory private to the virtual block; `bar` is the named barrier the 8 warps synchronise on (0 = __syncthreads of a 256-thread
+// block).  COHERENT selects L2-coherent activation loads (ld.global.cg) for use inside a kernel whose other CTAs produced X.
+template <int M, bool LSTM, bool COHERENT>
+__device__ __forceinline__ void rc_gemv_vblock(const RcLinear& a, int ksplit, int vb, int warp, int lane, float (*part)[4 * M], int cnt, int bar) {
     const int jpb = 8 / ksplit;
-    const int job = blockIdx.x * jpb + warp / ksplit;
+    const int job = vb * jpb + warp / ksplit;
     const int ks = warp % ksplit;
     const int njobs = a.Nw >> 2;
     const int K = a.K1 + a.K2;
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(256) rc_gemv_kernel(RcLinear a, int ksplit) {
                 if (rowid[m] >= 0) {
                     const float* xp = (k < a.K1) ? (a.X + (size_t)rowid[m] * a.ldx + k)
                                                  : (a.X2 + (size_t)rowid[m] * a.ldx2 + (k - a.K1));
-                    xv = __ldg(reinterpret_cast<const float4*>(xp));
+                    xv = COHERENT ? __ldcg(reinterpret_cast<const float4*>(xp)) : __ldg(reinterpret_cast<const float4*>(xp));
                 }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -109,35 +111,45 @@ __global__ void __launch_bounds__(256) rc_gemv_kernel(RcLinear a, int ksplit) {
 #pragma unroll
             for (int m = 0; m < M; ++m) part[warp][r * M + m] = acc[r][m];
     }
-    __syncthreads();
-    if (ks != 0 || job >= njobs || lane >= cnt) return;
-    const int m = lane;
-    const int row = a.rows[m];
-    float tot[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        float s = 0.f;
-        for (int q = 0; q < ksplit; ++q) s += part[warp + q][r * M + m];
-        tot[r] = s;
-    }
-    if (LSTM) {
-        const float4 b = *reinterpret_cast<const float4*>(a.bias + job * 4);
-        const size_t idx = (size_t)row * a.H + job;
-        float cn, hn;
-        rc_lstm_cell(tot[0] + b.x, tot[1] + b.y, tot[2] + b.z, tot[3] + b.w, a.C[idx], cn, hn);
-        a.C[idx] = cn;
-        a.Hout[idx] = hn;
-    } else {
+    if (bar == 0) __syncthreads(); else asm volatile("bar.sync %0, 256;" ::"r"(bar) : "memory");
+    if (!(ks != 0 || job >= njobs || lane >= cnt)) {
+        const int m = lane;
+        const int row = a.rows[m];
+        float tot[4];
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const int n = job * 4 + r;
-            if (n < a.N) {
-                float y = tot[r] + a.bias[n];
-                if (a.relu) y = fmaxf(y, 0.f);
-                a.Y[(size_t)row * a.ldy + n] = y;
+            float s = 0.f;
+            for (int q = 0; q < ksplit; ++q) s += part[warp + q][r * M + m];
+            tot[r] = s;
+        }
+        if (LSTM) {
+            const float4 b = *reinterpret_cast<const float4*>(a.bias + job * 4);
+            const size_t idx = (size_t)row * a.H + job;
+            float cn, hn;
+            const float cprev = COHERENT ? __ldcg(a.C + idx) : a.C[idx];
+            rc_lstm_cell(tot[0] + b.x, tot[1] + b.y, tot[2] + b.z, tot[3] + b.w, cprev, cn, hn);
+            a.C[idx] = cn;
+            a.Hout[idx] = hn;
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int n = job * 4 + r;
+                if (n < a.N) {
+                    float y = tot[r] + a.bias[n];
+                    if (a.relu) y = fmaxf(y, 0.f);
+                    a.Y[(size_t)row * a.ldy + n] = y;
+                }
             }
         }
     }
+}
+
+template <int M, bool LSTM>
+__global__ void __launch_bounds__(256) rc_gemv_kernel(RcLinear a, int ksplit) {
+    __shared__ float part[8][4 * M];
+    const int cnt = min(*a.count, M);
+    if (cnt == 0) return;
+    rc_gemv_vblock<M, LSTM, false>(a, ksplit, blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, part, cnt, 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -245,7 +257,7 @@ __global__ void __launch_bounds__(256, 2) rc_gemm_kernel(RcLinear a) {
 
 // h <- h_new for the rows of a list, both LSTM layers (the GEMM reads all of h_prev while it writes h_new, so the
 // new hidden state is committed by a separate launch).
-__global__ void __launch_bounds__(256) rc_commit_kernel(const float* __restrict__ hn0, const float* __restrict__ hn1,
+static __global__ void __launch_bounds__(256) rc_commit_kernel(const float* __restrict__ hn0, const float* __restrict__ hn1,
                                                          float* __restrict__ h0, float* __restrict__ h1, int H,
                                                          const int* __restrict__ rows, const int* __restrict__ count) {
     const int cnt = *count;

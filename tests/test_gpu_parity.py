@@ -306,3 +306,50 @@ torch.save({'p': p.cpu(), 't': t.cpu(), 'ps': ps.cpu(), 'ts': ts.cpu()}, sys.arg
         outs[mode] = torch.load(f)
     for k in ('p', 't', 'ps', 'ts'):
         assert torch.equal(outs['warp'][k], outs['scalar'][k]), k
+
+
+def test_stream_kernel_matches_multi_kernel(rb, body, golden_dir, tmp_path):
+    """forward_online through the single cooperative frame kernel (stream.cu) must equal the multi-kernel path bit for bit
+    (same GEMV routine, same reduction order), on sequences that cover first_frame / first_tran starts and every branch."""
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, torch, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import robustcap_b200 as rb
+from robustcap_b200 import synthetic
+from test_oracle_golden import load
+assets = synthetic.write_assets(synthetic.default_asset_root(), 0)
+out = {}
+body = rb.ParametricModel(assets['smpl_file'])
+for name, variant, start in (('mixed_ff', 'default', 'ff'), ('contact_mixed_ft', 'contact', 'ft'), ('contact_low_ff', 'contact', 'ff'), ('occl_ft', 'default', 'ft')):
+    g = load(%r, 'online_%%s.npz' %% name)
+    net = rb.Net(body)
+    net.load_state_dict(synthetic.make_state_dict(0, variant))
+    rb.Net.gravityc = g['gravity'].clone()
+    ps, ts = [], []
+    for t in range(g['j2dc'].shape[0]):
+        kw = {}
+        if t == 0 and start == 'ff': kw['first_frame'] = True
+        if t == 0 and start == 'ft': kw['first_tran'] = torch.tensor([0., 0., 4.])
+        p, tr = net.forward_online(g['j2dc'][t], g['accc'][t], g['oric'][t], **kw)
+        ps.append(p); ts.append(tr)
+    out[name] = (torch.stack(ps), torch.stack(ts))
+    del net
+torch.save(out, sys.argv[1])
+''' % (repo, os.path.join(repo, 'tests'), golden_dir)
+    outs = {}
+    for mode in ('stream', 'multi'):
+        env = dict(os.environ)
+        env.pop('RC_NO_STREAM_KERNEL', None)
+        if mode == 'multi':
+            env['RC_NO_STREAM_KERNEL'] = '1'
+        f = str(tmp_path / (mode + '.pt'))
+        subprocess.check_call([sys.executable, '-c', script, f], env=env)
+        outs[mode] = torch.load(f)
+    for name in outs['stream']:
+        g = load(golden_dir, 'online_%s.npz' % name)
+        assert torch.equal(outs['stream'][name][0], outs['multi'][name][0]), name
+        assert torch.equal(outs['stream'][name][1], outs['multi'][name][1]), name
+        assert pose_angle(outs['stream'][name][0], g['pose']).max().item() < RAD_TOL
