@@ -60,19 +60,116 @@ __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& epoch) {
     __syncthreads();
 }
 
+// NI independent GEMV items (virtual-block indices vb0, vb0 + stride, ...) of one layer processed together by one virtual block:
+// all weight loads of the NI items are issued before any is consumed, so HBM latency is paid once per batch instead of once per
+// item.  Per item the arithmetic is exactly rc_gemv_vblock<1, LSTM, true> (same K split, FMA order, shuffle tree, partial order).
+template <bool LSTM, int NI>
+__device__ __forceinline__ void gemv_items(const RcLinear& a, int ksplit, int vb0, int stride, int nvb, int w, int lane,
+                                           float (*part)[8][4], int bar) {
+    const int jpb = 8 / ksplit, ks = w % ksplit, njobs = a.Nw >> 2, K = a.K1 + a.K2;
+    int job[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int vb = vb0 + i * stride;
+        job[i] = (vb < nvb) ? vb * jpb + w / ksplit : njobs;
+    }
+    float acc[NI][4];
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[i][r] = 0.f;
+    for (int k = (ks * 32 + lane) * 4; k < K; k += ksplit * 128) {
+        float4 wv[NI][4];
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+            if (job[i] < njobs) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) wv[i][r] = rc_ldg_stream(a.W + (size_t)(job[i] * 4 + r) * K + k);
+            }
+        const float* xp = (k < a.K1) ? (a.X + k) : (a.X2 + (k - a.K1));
+        const float4 xv = __ldcg(reinterpret_cast<const float4*>(xp));
+#pragma unroll
+        for (int i = 0; i < NI; ++i)
+            if (job[i] < njobs) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    acc[i][r] = fmaf(wv[i][r].x, xv.x, acc[i][r]);
+                    acc[i][r] = fmaf(wv[i][r].y, xv.y, acc[i][r]);
+                    acc[i][r] = fmaf(wv[i][r].z, xv.z, acc[i][r]);
+                    acc[i][r] = fmaf(wv[i][r].w, xv.w, acc[i][r]);
+                }
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float v = acc[i][r];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) part[i][w][r] = v;
+        }
+    asm volatile("bar.sync %0, 256;" ::"r"(bar) : "memory");
+    if (ks == 0 && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            if (job[i] >= njobs) continue;
+            float tot[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float sacc = 0.f;
+                for (int q = 0; q < ksplit; ++q) sacc += part[i][w + q][r];
+                tot[r] = sacc;
+            }
+            if (LSTM) {
+                const float4 b = *reinterpret_cast<const float4*>(a.bias + job[i] * 4);
+                float cn, hn;
+                rc_lstm_cell(tot[0] + b.x, tot[1] + b.y, tot[2] + b.z, tot[3] + b.w, __ldcg(a.C + job[i]), cn, hn);
+                a.C[job[i]] = cn;
+                a.Hout[job[i]] = hn;
+            } else {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int n = job[i] * 4 + r;
+                    if (n < a.N) {
+                        float y = tot[r] + a.bias[n];
+                        if (a.relu) y = fmaxf(y, 0.f);
+                        a.Y[n] = y;
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("bar.sync %0, 256;" ::"r"(bar) : "memory");                  // `part` is reused by the next batch
+}
+
+constexpr int kSkNI = 4;
+
+template <bool LSTM>
+__device__ __forceinline__ void run_one(const RcLinear* L, int first_slot, float (*part)[8][4]) {
+    if (!L) return;
+    const int v = threadIdx.x >> 8, w = (threadIdx.x >> 5) & 7, lane = threadIdx.x & 31;
+    const int nslots = gridDim.x * kSkVb;
+    int slot = blockIdx.x * kSkVb + v - first_slot;                          // rotate so that two layers start on different slots
+    if (slot < 0) slot += nslots;
+    const int ks = rc_gemv_ksplit(L->K1 + L->K2);
+    const int jpb = 8 / ks;
+    const int nvb = ((L->Nw >> 2) + jpb - 1) / jpb;
+    for (int vb0 = slot; vb0 < nvb; vb0 += nslots * kSkNI)
+        gemv_items<LSTM, kSkNI>(*L, ks, vb0, nslots, nvb, w, lane, part + v * kSkNI, v + 1);
+}
+
 // All CTAs share the virtual blocks of up to two independent layers (A first: the heavier one).
 template <bool LSTM>
 __device__ __forceinline__ void run_layers(const RcLinear* A, const RcLinear* B, float (*part)[8][4]) {
-    const int v = threadIdx.x >> 8, w = (threadIdx.x >> 5) & 7, lane = threadIdx.x & 31;
-    const int slot = blockIdx.x * kSkVb + v, nslots = gridDim.x * kSkVb;
-    const int ksA = A ? rc_gemv_ksplit(A->K1 + A->K2) : 1, ksB = B ? rc_gemv_ksplit(B->K1 + B->K2) : 1;
-    const int nA = A ? ((A->Nw >> 2) + 8 / ksA - 1) / (8 / ksA) : 0;
-    const int nB = B ? ((B->Nw >> 2) + 8 / ksB - 1) / (8 / ksB) : 0;
-    for (int idx = slot; idx < nA + nB; idx += nslots) {
-        if (idx < nA) rc_gemv_vblock<1, LSTM, true>(*A, ksA, idx, w, lane, part[v], 1, v + 1);
-        else rc_gemv_vblock<1, LSTM, true>(*B, ksB, idx - nA, w, lane, part[v], 1, v + 1);
-        asm volatile("bar.sync %0, 256;" ::"r"(v + 1) : "memory");            // `part` is reused by the next item
+    run_one<LSTM>(A, 0, part);
+    // B's items start where A's last partial round ended, so the tail slots of A and the head slots of B differ
+    int off = 0;
+    if (A) {
+        const int ks = rc_gemv_ksplit(A->K1 + A->K2), jpb = 8 / ks;
+        off = (((A->Nw >> 2) + jpb - 1) / jpb) % (gridDim.x * kSkVb);
     }
+    run_one<LSTM>(B, off, part);
 }
 
 __device__ __forceinline__ void commit_h(const float* hn, float* h, int H) {     // h <- h_new, one warp
@@ -99,7 +196,7 @@ __device__ __forceinline__ void run_group(const SkNet* A, const SkNet* B, bool l
 }
 
 __global__ void __launch_bounds__(kSkThreads, 1) rc_stream_kernel(const __grid_constant__ SkArgs a) {
-    __shared__ float part[kSkVb][8][4];
+    __shared__ float part[kSkVb * kSkNI][8][4];
     __shared__ RcPrepWarpSmem sprep;
     __shared__ RcKinWarpSmem skin;
     __shared__ RcModelConst Ms;
