@@ -35,12 +35,18 @@ struct SkArgs {
     float *X2, *X3, *X4, *X6, *X7, *XI, *Y3, *Y6, *Y7, *Y8, *I3, *rcr, *conf, *lerpw, *gravity;
     int* flags;        // [0] frame flags, [1] need_init
     unsigned* bar;     // grid barrier counter, zeroed by the host before the launch
+    unsigned long long* ts;   // optional phase timestamps (RC_STREAM_TS=1), CTA 0 thread 0
 };
 
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ void stamp(unsigned long long* ts, int& n) {
+    if (ts && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); ts[n] = t; }
+    ++n;
 }
 
 __device__ __forceinline__ void grid_sync(unsigned* bar, unsigned& epoch) {
@@ -199,7 +205,9 @@ __global__ void __launch_bounds__(kSkThreads, 1) rc_stream_kernel(const __grid_c
     __shared__ RcKinWarpSmem skin;
     __shared__ RcModelConst Ms;
     unsigned epoch = 0;
+    int nts = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    stamp(a.ts, nts);
     const StepIO& io = a.io;
 
     // ---- prep (sig_mp.py:138-153) -----------------------------------------------------------------------------------
@@ -218,6 +226,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) rc_stream_kernel(const __grid_c
         }
     }
     grid_sync(a.bar, epoch);
+    stamp(a.ts, nts);   // 1: after prep
     const int f = __ldcg(a.flags);
     const bool hi = (f & RC_F_HI) != 0, ff = (f & RC_F_FIRST_FRAME) != 0, r6b = (f & RC_F_R6B) != 0, late = (f & RC_F_LATE) != 0;
 
@@ -230,6 +239,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) rc_stream_kernel(const __grid_c
         run_group(r6b ? &a.net[NET6] : &a.net[NET3], r6b ? &a.net[NET3] : nullptr, true, a.bar, epoch, part);
     }
 
+    stamp(a.ts, nts);   // 2: after groups 1-2
     // ---- mid: camera->root rotation of the vision joints and the confidence lerp (:154-167) ------------------------------------
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         float r[9], lw[2], ji[69], jc[69], out[69];
@@ -241,9 +251,11 @@ __global__ void __launch_bounds__(kSkThreads, 1) rc_stream_kernel(const __grid_c
     }
     grid_sync(a.bar, epoch);
 
+    stamp(a.ts, nts);   // 3: after mid
     // ---- pose and contact nets (:169-170) -------------------------------------------------------------------------------
     run_group(&a.net[NET7], &a.net[NET8], true, a.bar, epoch, part);
 
+    stamp(a.ts, nts);   // 4: after group 3
     // ---- kin (:173-273) ------------------------------------------------------------------------------------------------------
     if (blockIdx.x == 0 && warp == 0) {
         float r[9], g[3], ft[3] = {0.f, 0.f, 0.f}, y8[2], vr[3], pc[3];
@@ -259,6 +271,7 @@ __global__ void __launch_bounds__(kSkThreads, 1) rc_stream_kernel(const __grid_c
     }
     grid_sync(a.bar, epoch);
 
+    stamp(a.ts, nts);   // 5: after kin
     // ---- rnn2.init_net re-seed on the first c >= hi (:178-183) --------------------------------------------------------------
     if (__ldcg(a.flags + 1)) {
         for (int l = 0; l < 3; ++l) { run_layers<false>(&a.init[l], nullptr, part); grid_sync(a.bar, epoch); }
@@ -271,14 +284,18 @@ __global__ void __launch_bounds__(kSkThreads, 1) rc_stream_kernel(const __grid_c
         }
     }
     // ---- vision updater keeps rnn6 / rnn4 warm on the synthetic key points (:263-271) -----------------------------------------
+    stamp(a.ts, nts);   // 6: after init
     if (late) run_group(&a.net[NET4], &a.net[NET6], false, a.bar, epoch, part);
+    stamp(a.ts, nts);   // 7: end
 }
 
 }  // namespace
 
 bool rc_stream_supported(const rc_state* s) {
-    static const bool off = getenv("RC_NO_STREAM_KERNEL") != nullptr;
-    return !off && s->B == 1;
+    // Opt-in (RC_STREAM_KERNEL=1): validated bit-exact against the multi-kernel path, but measured 150 us per frame vs 141 us for
+    // the 2-stream CUDA-graph path — both are bound by the ~18-deep chain of dependent layers (6-8 us per phase), not by HBM.
+    static const bool on = getenv("RC_STREAM_KERNEL") != nullptr;
+    return on && s->B == 1;
 }
 
 int rc_stream_frame(rc_state* s, const StepIO& io, int any_first_frame, void* stream) {
@@ -295,7 +312,7 @@ int rc_stream_frame(rc_state* s, const StepIO& io, int any_first_frame, void* st
         grid = sms;
     }
     if (!s->sk_bar) {
-        RC_CUDA(cudaMalloc(&s->sk_bar, 64));
+        RC_CUDA(cudaMalloc(&s->sk_bar, 256));
         const int init[8] = {0, 1, 0, 0, 0, 0, 0, 0};  // rows = {0}, count = 1, flags
         RC_CUDA(cudaMalloc(&s->sk_rows, sizeof(init)));
         RC_CUDA(cudaMemcpy(s->sk_rows, init, sizeof(init), cudaMemcpyHostToDevice));
@@ -342,9 +359,21 @@ int rc_stream_frame(rc_state* s, const StepIO& io, int any_first_frame, void* st
     }
     a.X2 = s->X2; a.X3 = s->X3; a.X4 = s->X4; a.X6 = s->X6; a.X7 = s->X7; a.XI = s->XI; a.Y3 = s->Y3; a.Y6 = s->Y6; a.Y7 = s->Y7; a.Y8 = s->Y8;
     a.I3 = s->I3; a.rcr = s->rcr; a.conf = s->conf; a.lerpw = s->lerpw; a.gravity = s->gravity; a.flags = s->flags_sk; a.bar = s->sk_bar;
+    static const bool want_ts = getenv("RC_STREAM_TS") != nullptr;
+    a.ts = want_ts ? reinterpret_cast<unsigned long long*>(s->sk_bar + 4) : nullptr;
     RC_CUDA(cudaMemsetAsync(s->sk_bar, 0, sizeof(unsigned), st));
     void* args[1] = {&a};
     RC_CUDA(cudaLaunchCooperativeKernel((const void*)rc_stream_kernel, dim3(grid), dim3(kSkThreads), args, 0, st));
     g_rc_launches.fetch_add(1, std::memory_order_relaxed);
+    if (want_ts) {
+        static int printed = 0;
+        unsigned long long h[8];
+        RC_CUDA(cudaStreamSynchronize(st));
+        RC_CUDA(cudaMemcpy(h, s->sk_bar + 4, sizeof(h), cudaMemcpyDeviceToHost));
+        if (printed++ % 50 == 10)
+            fprintf(stderr, "[stream kernel us] prep %.1f | groups1-2 %.1f | mid %.1f | group3 %.1f | kin %.1f | init %.1f | late %.1f | total %.1f\n",
+                    (h[1] - h[0]) * 1e-3, (h[2] - h[1]) * 1e-3, (h[3] - h[2]) * 1e-3, (h[4] - h[3]) * 1e-3, (h[5] - h[4]) * 1e-3,
+                    (h[6] - h[5]) * 1e-3, (h[7] - h[6]) * 1e-3, (h[7] - h[0]) * 1e-3);
+    }
     return RC_OK;
 }

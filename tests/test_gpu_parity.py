@@ -342,9 +342,9 @@ torch.save(out, sys.argv[1])
     outs = {}
     for mode in ('stream', 'multi'):
         env = dict(os.environ)
-        env.pop('RC_NO_STREAM_KERNEL', None)
-        if mode == 'multi':
-            env['RC_NO_STREAM_KERNEL'] = '1'
+        env.pop('RC_STREAM_KERNEL', None)
+        if mode == 'stream':
+            env['RC_STREAM_KERNEL'] = '1'
         f = str(tmp_path / (mode + '.pt'))
         subprocess.check_call([sys.executable, '-c', script, f], env=env)
         outs[mode] = torch.load(f)
