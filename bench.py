@@ -310,11 +310,13 @@ def main():
     # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
     dom_flop = fpr.value * 2 * B * T * args.steps
     dom_tflops = dom_flop / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
-    roofline = {'kernel': 'rc_lstm_tc_kernel (rnn4 fused LSTM layer [rows,2560]x[2560,5120]; tcgen05 kind::f16 on split-fp16 operands, '
-                          '3 MMAs per fp32-accurate product; the event pair also covers the row-gather/split pre-pass)', 'bound': 'tensor',
+    roofline = {'kernel': 'rc_tc_kernel<128,3,LSTM> (rnn4 fused LSTM layer [rows,2560]x[2560,5120]; tcgen05 kind::f16 on split-fp16 operands, '
+                          '3 MMAs per fp32-accurate product; CUDA events on its launch stream while the other lane runs concurrently)',
+                'bound': 'tensor',
                 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': dom_tflops / pk['tflops_sustained'], 'peak_source': 'bf16 sustained, of ' + pk['source'],
                 'traffic': dominant_traffic(), 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,
+                'tensor_pipe_frac': 3 * dom_tflops / pk['tflops_sustained'],   # 3 fp16 MMAs are issued per algorithmic fp32 product
                 'whole_path_tflops': FLOP_PER_FRAME * B * T / (ms_step * 1e-3) / 1e12,
                 'weight_stream_gbs': WEIGHT_BYTES * T / (ms_step * 1e-3) / 1e9}
     line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),

@@ -261,14 +261,14 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
         a.W = w.WL[l]; a.bias = w.bL[l]; a.N = 4 * w.H; a.Nw = 4 * w.H; a.Y = nullptr; a.ldy = 0; a.relu = 0;
         a.C = nb.c[l]; a.Hout = nb.hn[l];
         const bool prof = s->prof_on && ni == NET4;
-        if (prof) {
+        if (tc) RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
+        if (prof) {            // CUDA events right around the dominant GEMM launch, on the stream it is launched on
             if (s->prof_used + 2 > s->prof_ev.size()) {
                 for (int q = 0; q < 256; ++q) { cudaEvent_t e; RC_CUDA(cudaEventCreate(&e)); s->prof_ev.push_back(e); }
             }
             RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
         }
         if (tc) {
-            RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
             static const bool use_cluster = getenv("RC_TC_CLUSTER") != nullptr;      // experiment switch (measured slower)
             if (use_cluster && B > 128)
                 RC_TRY(rc_tc_lstm_layer_cluster(&s->mAhi64[lane][ni], &s->mAlo64[lane][ni], &w.mWhi64[l], &w.mWlo64[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
