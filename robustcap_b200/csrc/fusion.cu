@@ -188,9 +188,9 @@ __global__ void __launch_bounds__(256) rc_init_scatter_kernel(const float* __res
 }
 
 __global__ void rc_advance_kernel(int* d_t) { *d_t += 1; }
-__global__ void rc_reset_rows_kernel(RcRowState* rows, int B) {
+__global__ void rc_reset_rows_kernel(RcRowState* rows, int B, int created) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < B) rc_row_state_reset(&rows[b]);
+    if (b < B) rc_row_state_reset(&rows[b], created != 0);
 }
 
 // ---- host helpers ------------------------------------------------------------------------------------------------
@@ -613,7 +613,8 @@ int rc_state_reset(rc_state* s, void* stream) {
     RC_CUDA(cudaMemsetAsync(s->X6, 0, (size_t)s->B * RC_K6 * sizeof(float), st));
     RC_CUDA(cudaMemsetAsync(s->X4, 0, (size_t)s->B * RC_K4 * sizeof(float), st));
     RC_CUDA(cudaMemsetAsync(s->d_t, 0, sizeof(int), st));
-    RC_LAUNCH(rc_reset_rows_kernel, rc_cdiv(s->B, 128), 128, 0, stream, s->rows, s->B);
+    RC_LAUNCH(rc_reset_rows_kernel, rc_cdiv(s->B, 128), 128, 0, stream, s->rows, s->B, s->fresh ? 1 : 0);
+    s->fresh = false;
     RC_CHECK_LAUNCH();
     return RC_OK;
 }

@@ -49,6 +49,7 @@ struct rc_net {
 struct rc_state {
     const rc_net* net = nullptr;
     int B = 0;
+    bool fresh = true;                 // first reset after creation also zeroes the fields reset_states leaves alone
     std::vector<void*> allocs;
     NetBuf nb[NNETS];
     float *X2 = nullptr, *X3 = nullptr, *X4 = nullptr, *X6 = nullptr, *X7 = nullptr, *XI = nullptr;

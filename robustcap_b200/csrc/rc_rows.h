@@ -66,8 +66,11 @@ struct RcRowState {                   // mutable per-stream state other than the
     int vision_count;                 // update_vision_count
 };
 
-RC_HD void rc_row_state_reset(RcRowState* s) {
-    s->has_last = 0; s->floor_n = 0; s->first_reach = 1; s->vision_count = 0;
+// Net.reset_states (sig_mp.py:95-104).  update_vision_count is NOT among the fields the reference resets: it keeps counting
+// across sequences, so it is only zeroed when the state is created.
+RC_HD void rc_row_state_reset(RcRowState* s, bool created = false) {
+    s->has_last = 0; s->floor_n = 0; s->first_reach = 1;
+    if (created) s->vision_count = 0;
 }
 
 // torch's float32 mean over the 33 strided confidences: 4 interleaved partial sums, combined left to right

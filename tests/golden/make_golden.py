@@ -144,8 +144,9 @@ ONLINE_CASES = [
 ]
 
 
-def run_online(ref, sd, inp, start, record=None):
+def run_online(ref, sd, inp, start, record=None, live=False):
     Net = ref['Net']
+    Net.live = live                      # class attribute, set BEFORE construction (sig_mp.py:91-93) and read again on every frame (:229, :264)
     net = Net()
     net.load_state_dict(sd)
     net.eval()
@@ -171,20 +172,27 @@ def run_online(ref, sd, inp, start, record=None):
         trans.append(tr)
     for h in hooks:
         h.remove()
+    Net.live = False
     floor_n = len(net.floor_y)
     net.reset_states()
     return torch.stack(poses), torch.stack(trans), floor_n
 
 
+LIVE_CASES = [
+    ('live_mixed_ft', 0, 'contact', 'mixed', 31, 'first_tran', 72),
+    ('live_low_none', 0, 'default', 'low', 32, 'none', 40),
+]
+
+
 def gen_online(ref, out):
     cache = {}
-    for name, wseed, variant, conf, iseed, start, T in ONLINE_CASES:
+    for name, wseed, variant, conf, iseed, start, T in ONLINE_CASES + LIVE_CASES:
         key = (wseed, variant)
         if key not in cache:
             cache[key] = synthetic.make_state_dict(wseed, variant)
         inp = synthetic.make_inputs(1, T, seed=iseed, conf=conf)
         rec = []
-        pose, tran, floor_n = run_online(ref, cache[key], inp, start, rec)
+        pose, tran, floor_n = run_online(ref, cache[key], inp, start, rec, live=name.startswith('live_'))
         d = {'j2dc': inp['j2dc'][0], 'accc': inp['accc'][0], 'oric': inp['oric'][0], 'gravity': inp['gravity'],
              'pose': pose, 'tran': tran, 'floor_n': torch.tensor(floor_n)}
         # sub-net outputs in call order for the first 6 frames (debug aid: which net diverged first)

@@ -128,7 +128,7 @@ void hh_reset(void* p) {
     Harness* h = (Harness*)p;
     for (int i = 0; i < 6; ++i)
         for (int l = 0; l < 2; ++l) { h->nets[i].h[l].assign(h->nets[i].H, 0.f); h->nets[i].c[l].assign(h->nets[i].H, 0.f); }
-    rc_row_state_reset(&h->st);
+    rc_row_state_reset(&h->st, true);
     memset(h->sX4, 0, sizeof(h->sX4)); memset(h->sX6, 0, sizeof(h->sX6));
 }
 int hh_floor_n(void* p) { return ((Harness*)p)->st.floor_n; }

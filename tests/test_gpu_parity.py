@@ -103,10 +103,13 @@ def test_smpl_forward_kinematics(rb, body, golden_dir):
 _NETS = {}
 
 
-def get_net(rb, body, wseed, variant):
-    key = (wseed, variant)
+def get_net(rb, body, wseed, variant, live=False):
+    key = (wseed, variant, live)
     if key not in _NETS:
+        rb.Net.live = live              # class attribute, read at construction (thresholds) like the reference (sig_mp.py:91-93)
         net = rb.Net(body)
+        rb.Net.live = False
+        net.live = live                 # ... and on every frame (:229, :264)
         net.load_state_dict(get_sd(wseed, variant))
         _NETS[key] = net
     return _NETS[key]
@@ -125,7 +128,7 @@ def test_forward_online_golden(rb, body, golden_dir, case):
     """Streaming B=1 (GEMV kernels), frame by frame through Net.forward_online, vs the reference's outputs."""
     name, wseed, variant, conf, iseed, start, Tn = case
     g = load(golden_dir, 'online_%s.npz' % name)
-    net = get_net(rb, body, wseed, variant)
+    net = get_net(rb, body, wseed, variant, live=name.startswith('live_'))
     rb.Net.gravityc = g['gravity'].clone()
     net.reset_states()
     poses, trans = [], []

@@ -87,11 +87,12 @@ def _case_meta():
         'make_golden', os.path.join(os.path.dirname(__file__), 'golden', 'make_golden.py'))
     src = open(spec.origin).read()
     # parse ONLINE_CASES without importing the reference
-    start = src.index('ONLINE_CASES = [')
-    end = src.index(']\n', start) + 1
     ns = {}
-    exec(src[start:end], ns)
-    return ns['ONLINE_CASES']
+    for key in ('ONLINE_CASES = [', 'LIVE_CASES = ['):
+        start = src.index(key)
+        end = src.index(']\n', start) + 1
+        exec(src[start:end], ns)
+    return ns['ONLINE_CASES'] + ns['LIVE_CASES']
 
 
 ONLINE_CASES = _case_meta()
@@ -122,7 +123,7 @@ def test_online(golden_dir, assets, case, impl):
     inp = synthetic.make_inputs(1, Tn, seed=iseed, conf=conf)
     assert torch.equal(inp['j2dc'][0], g['j2dc']) and torch.equal(inp['oric'][0], g['oric'])
     body = K.BodyOracle(assets['smpl_file'])
-    net = FusionOracle(get_sd(wseed, variant), body, lstm_impl=impl)
+    net = FusionOracle(get_sd(wseed, variant), body, lstm_impl=impl, live=name.startswith('live_'))
     kw = {'first_frame': True} if start == 'first_frame' else (
         {'first_tran': torch.tensor([0., 0., 4.])} if start == 'first_tran' else {})
     trace = []
