@@ -250,33 +250,54 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
     a.W = w.W1; a.bias = w.b1; a.N = w.H; a.Nw = w.H; a.Y = nb.a1; a.ldy = w.H; a.relu = 1; a.H = w.H;
     const bool tc = s->net->gemm_mode == 1 && s->tc_ready && B > 8;
     if (tc) {
-        RC_TRY(rc_tc_split_rows(X, w.K1, nullptr, 0, w.K1, 0, w.K1p, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
-        RC_TRY(rc_tc_linear(&s->mA1hi[lane][ni], &s->mA1lo[lane][ni], &w.mW1hi, &w.mW1lo, w.b1, nb.a1, w.H, w.H, w.K1p, 1, rows, count, B, stream));
-    } else {
-        RC_TRY(launch_linear(a, B, false, stream));
+        // tensor-core path: one gather/split pre-pass, then lin1 -> LSTM0 -> LSTM1 -> commit -> lin2, every epilogue writing the
+        // next GEMM's A operand directly (split fp16 halves, compact row order)
+        uint16_t **Ah = s->Ahi[lane], **Al = s->Alo[lane];
+        const RcSplitSeg segs[3] = {
+            {X, w.K1, w.K1, w.K1p, 0, w.K1p, Ah[0], Al[0]},                      // linear1 input
+            {nb.h[0], w.H, w.H, w.H, w.H, 2 * w.H, Ah[1], Al[1]},                // h_prev of layer 0 -> columns [H, 2H) of buf 1
+            {nb.h[1], w.H, w.H, w.H, w.H, 2 * w.H, Ah[2], Al[2]}};               // h_prev of layer 1 -> columns [H, 2H) of buf 2
+        RC_TRY(rc_tc_split_pass(segs, 3, rows, count, B, stream));
+        RC_TRY(rc_tc_linear(&s->mA0hi[lane][ni], &s->mA0lo[lane][ni], &w.mW1hi, &w.mW1lo, w.b1, nullptr, 0, w.H, w.K1p, 1, rows, count, B, stream,
+                            Ah[1], Al[1], 2 * w.H));
+        for (int l = 0; l < 2; ++l) {
+            const bool prof = s->prof_on && ni == NET4;
+            if (prof) {            // CUDA events right around the dominant GEMM launch, on the stream it is launched on
+                if (s->prof_used + 2 > s->prof_ev.size()) {
+                    for (int q = 0; q < 256; ++q) { cudaEvent_t e; RC_CUDA(cudaEventCreate(&e)); s->prof_ev.push_back(e); }
+                }
+                RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
+            }
+            void* nh = (l == 0) ? (void*)Ah[2] : (Y ? (void*)Ah[1] : nullptr);
+            void* nl = (l == 0) ? (void*)Al[2] : (Y ? (void*)Al[1] : nullptr);
+            const int np = (l == 0) ? 2 * w.H : w.H;
+            RC_TRY(rc_tc_lstm_layer(l == 0 ? &s->mA1hi[lane][ni] : &s->mA2hi[lane][ni], l == 0 ? &s->mA1lo[lane][ni] : &s->mA2lo[lane][ni],
+                                    &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream, nh, nl, np));
+            if (prof) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
+        }
+        {
+            const long long work = (long long)B * (w.H / 4);
+            const int grid = (int)std::min<long long>(rc_cdiv(work, 256), 1184);
+            RC_LAUNCH(rc_commit_kernel, grid, 256, 0, stream, nb.hn[0], nb.hn[1], nb.h[0], nb.h[1], w.H, rows, count);
+            RC_CHECK_LAUNCH();
+        }
+        if (Y) RC_TRY(rc_tc_linear(&s->mA1Hhi[lane][ni], &s->mA1Hlo[lane][ni], &w.mW2hi, &w.mW2lo, w.b2, Y, ldy, w.out, w.H, 0, rows, count, B, stream));
+        return RC_OK;
     }
+    RC_TRY(launch_linear(a, B, false, stream));
     // LSTM layers
     for (int l = 0; l < 2; ++l) {
         a.X = (l == 0) ? nb.a1 : nb.hn[0]; a.ldx = w.H; a.X2 = nb.h[l]; a.ldx2 = w.H; a.K1 = w.H; a.K2 = w.H;
         a.W = w.WL[l]; a.bias = w.bL[l]; a.N = 4 * w.H; a.Nw = 4 * w.H; a.Y = nullptr; a.ldy = 0; a.relu = 0;
         a.C = nb.c[l]; a.Hout = nb.hn[l];
         const bool prof = s->prof_on && ni == NET4;
-        if (tc) RC_TRY(rc_tc_split_rows(a.X, a.ldx, a.X2, a.ldx2, a.K1, a.K2, 2 * w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
-        if (prof) {            // CUDA events right around the dominant GEMM launch, on the stream it is launched on
+        if (prof) {
             if (s->prof_used + 2 > s->prof_ev.size()) {
                 for (int q = 0; q < 256; ++q) { cudaEvent_t e; RC_CUDA(cudaEventCreate(&e)); s->prof_ev.push_back(e); }
             }
             RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
         }
-        if (tc) {
-            static const bool use_cluster = getenv("RC_TC_CLUSTER") != nullptr;      // experiment switch (measured slower)
-            if (use_cluster && B > 128)
-                RC_TRY(rc_tc_lstm_layer_cluster(&s->mAhi64[lane][ni], &s->mAlo64[lane][ni], &w.mWhi64[l], &w.mWlo64[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
-            else
-                RC_TRY(rc_tc_lstm_layer(&s->mAhi[lane][ni], &s->mAlo[lane][ni], &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream));
-        } else {
-            RC_TRY(launch_linear(a, B, true, stream));
-        }
+        RC_TRY(launch_linear(a, B, true, stream));
         if (prof) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     }
     {
@@ -288,12 +309,7 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
     if (Y) {
         a.X = nb.hn[1]; a.ldx = w.H; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.H; a.K2 = 0;
         a.W = w.W2; a.bias = w.b2; a.N = w.out; a.Nw = w.out4; a.Y = Y; a.ldy = ldy; a.relu = 0; a.C = nullptr; a.Hout = nullptr;
-        if (tc) {
-            RC_TRY(rc_tc_split_rows(nb.hn[1], w.H, nullptr, 0, w.H, 0, w.H, rows, count, B, s->Ahi[lane], s->Alo[lane], stream));
-            RC_TRY(rc_tc_linear(&s->mA2hi[lane][ni], &s->mA2lo[lane][ni], &w.mW2hi, &w.mW2lo, w.b2, Y, ldy, w.out, w.H, 0, rows, count, B, stream));
-        } else {
-            RC_TRY(launch_linear(a, B, false, stream));
-        }
+        RC_TRY(launch_linear(a, B, false, stream));
     }
     return RC_OK;
 }
@@ -543,17 +559,19 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
         for (int i = 0; i < NNETS; ++i) Hmax = std::max(Hmax, net->nets[i].H);
         s->tc_ready = true;
         for (int ln = 0; ln < 2 && rc == RC_OK; ++ln) {
-            rc = dev_alloc(s->allocs, &s->Ahi[ln], (size_t)Bpad * 2 * Hmax);
-            if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->Alo[ln], (size_t)Bpad * 2 * Hmax);
+            for (int q = 0; q < 3 && rc == RC_OK; ++q) {
+                rc = dev_alloc(s->allocs, &s->Ahi[ln][q], (size_t)Bpad * 2 * Hmax);
+                if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->Alo[ln][q], (size_t)Bpad * 2 * Hmax);
+                if (rc == RC_OK) { cudaMemset(s->Ahi[ln][q], 0, (size_t)Bpad * 2 * Hmax * 2); cudaMemset(s->Alo[ln][q], 0, (size_t)Bpad * 2 * Hmax * 2); }
+            }
             if (rc != RC_OK) break;
-            cudaMemset(s->Ahi[ln], 0, (size_t)Bpad * 2 * Hmax * 2);
-            cudaMemset(s->Alo[ln], 0, (size_t)Bpad * 2 * Hmax * 2);
             for (int i = 0; i < NNETS && s->tc_ready; ++i) {
                 const NetDev& d = net->nets[i];
-                if (rc_tc_make_map(&s->mAhi64[ln][i], s->Ahi[ln], Bpad, 2 * d.H, 64) != RC_OK || rc_tc_make_map(&s->mAlo64[ln][i], s->Alo[ln], Bpad, 2 * d.H, 64) != RC_OK ||
-                    rc_tc_make_map(&s->mAhi[ln][i], s->Ahi[ln], Bpad, 2 * d.H, 128) != RC_OK || rc_tc_make_map(&s->mAlo[ln][i], s->Alo[ln], Bpad, 2 * d.H, 128) != RC_OK ||
-                    rc_tc_make_map(&s->mA1hi[ln][i], s->Ahi[ln], Bpad, d.K1p, 128) != RC_OK || rc_tc_make_map(&s->mA1lo[ln][i], s->Alo[ln], Bpad, d.K1p, 128) != RC_OK ||
-                    rc_tc_make_map(&s->mA2hi[ln][i], s->Ahi[ln], Bpad, d.H, 128) != RC_OK || rc_tc_make_map(&s->mA2lo[ln][i], s->Alo[ln], Bpad, d.H, 128) != RC_OK)
+                auto mk = [&](RcTensorMap* m, const void* base, int K) { return rc_tc_make_map(m, base, Bpad, K, 128) == RC_OK; };
+                if (!mk(&s->mA0hi[ln][i], s->Ahi[ln][0], d.K1p) || !mk(&s->mA0lo[ln][i], s->Alo[ln][0], d.K1p) ||
+                    !mk(&s->mA1hi[ln][i], s->Ahi[ln][1], 2 * d.H) || !mk(&s->mA1lo[ln][i], s->Alo[ln][1], 2 * d.H) ||
+                    !mk(&s->mA1Hhi[ln][i], s->Ahi[ln][1], d.H) || !mk(&s->mA1Hlo[ln][i], s->Alo[ln][1], d.H) ||
+                    !mk(&s->mA2hi[ln][i], s->Ahi[ln][2], 2 * d.H) || !mk(&s->mA2lo[ln][i], s->Alo[ln][2], 2 * d.H))
                     s->tc_ready = false;
             }
         }
@@ -800,8 +818,8 @@ int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* x
     const int* count = s->counts + L_ALL;
     if (mode == 1) {
         if (!(s->tc_ready && B > 8)) { rc_set_error("tensor-core path not available for this state"); return RC_ERR_STATE; }
-        RC_TRY(rc_tc_split_rows(x, w.H, hprev, w.H, w.H, w.H, 2 * w.H, rows, count, B, s->Ahi[0], s->Alo[0], stream));
-        RC_TRY(rc_tc_lstm_layer(&s->mAhi[0][ni], &s->mAlo[0][ni], &w.mWhi[layer], &w.mWlo[layer], w.bL[layer], c, hout, w.H, rows, count, B, stream));
+        RC_TRY(rc_tc_split_rows(x, w.H, hprev, w.H, w.H, w.H, 2 * w.H, rows, count, B, s->Ahi[0][1], s->Alo[0][1], stream));
+        RC_TRY(rc_tc_lstm_layer(&s->mA1hi[0][ni], &s->mA1lo[0][ni], &w.mWhi[layer], &w.mWlo[layer], w.bL[layer], c, hout, w.H, rows, count, B, stream));
     } else {
         RcLinear a;
         memset(&a, 0, sizeof(a));

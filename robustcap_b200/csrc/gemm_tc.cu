@@ -125,8 +125,26 @@ struct TcArgs {
     const int* rows;       // row list (stream indices); compact row i of the A operand belongs to stream rows[i]
     const int* count;
     int H, K;
+    __half* nAhi; __half* nAlo; int npitch;   // optional: the outputs, split into fp16 halves, written as rows of the NEXT GEMM's A operand
     int dbg;               // timing experiments only: 1 = skip the MMAs, 2 = skip the TMA loads (results are garbage)
 };
+
+// x[0..N) -> (hi, lo) fp16 halves exactly as rc_split_rows_kernel does, 16-byte stores (N = 8)
+template <int N>
+__device__ __forceinline__ void tc_store_split(const float* x, __half* Ahi, __half* Alo, size_t off) {
+    static_assert(N == 8, "one 16-byte store per half");
+    __half2 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half h0 = __float2half_rn(x[2 * i]), h1 = __float2half_rn(x[2 * i + 1]);
+        const __half l0 = __float2half_rn((x[2 * i] - __half2float(h0)) * 2048.f);
+        const __half l1 = __float2half_rn((x[2 * i + 1] - __half2float(h1)) * 2048.f);
+        h[i] = __halves2half2(h0, h1);
+        l[i] = __halves2half2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(Ahi + off) = *reinterpret_cast<const uint4*>(h);
+    *reinterpret_cast<uint4*>(Alo + off) = *reinterpret_cast<const uint4*>(l);
+}
 
 // Epilogue shared by the tcgen05 kernels: 8 warps (2 per TMEM lane quarter, each taking half of the BN columns).  Thread =
 // one output row.  The cell state of the row is prefetched with 128-bit loads BEFORE the accumulators are waited for (the
@@ -194,16 +212,22 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& a, uint32_t tmem_base,
             *reinterpret_cast<float4*>(a.C + idx + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
             *reinterpret_cast<float4*>(a.Hout + idx) = make_float4(hn[0], hn[1], hn[2], hn[3]);
             *reinterpret_cast<float4*>(a.Hout + idx + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            if (a.nAhi) tc_store_split<8>(hn, a.nAhi, a.nAlo, (size_t)mrow * a.npitch + (nb >> 2));
         } else {
             float* yrow = a.Y + (size_t)row * a.ldy;
-            const bool vec = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && (nb + 32 <= a.N);
+            const bool vec = ((a.ldy & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.Y) & 15) == 0) && (nb + 32 <= a.N);   // Y may be null when only the split copy is wanted
             if (vec) {
 #pragma unroll
                 for (int e = 0; e < 32; e += 4) {
                     const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + nb + e));
                     float4 y = make_float4(acc[e] + b.x, acc[e + 1] + b.y, acc[e + 2] + b.z, acc[e + 3] + b.w);
                     if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-                    *reinterpret_cast<float4*>(yrow + nb + e) = y;
+                    if (a.Y) *reinterpret_cast<float4*>(yrow + nb + e) = y;
+                    acc[e] = y.x; acc[e + 1] = y.y; acc[e + 2] = y.z; acc[e + 3] = y.w;
+                }
+                if (a.nAhi) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 8) tc_store_split<8>(acc + e, a.nAhi, a.nAlo, (size_t)mrow * a.npitch + nb + e);
                 }
             } else {
 #pragma unroll
@@ -451,6 +475,37 @@ __global__ void __launch_bounds__(256) rc_split_rows_kernel(const float* __restr
     }
 }
 
+// One pre-pass per sub-net pass: every operand that does not come out of a GEMM epilogue is gathered / split here in one launch
+// (linear1 input X -> A0, h_prev of layer 0 -> second half of A1's rows, h_prev of layer 1 -> second half of A2's rows).
+struct SplitSeg { const float* src; int ld; int K; int Kout; int col0; int pitch; __half* hi; __half* lo; };
+struct SplitPassArgs { SplitSeg seg[3]; int nseg; const int* rows; const int* count; };
+
+__global__ void __launch_bounds__(256) rc_split_pass_kernel(SplitPassArgs a) {
+    const int cnt = *a.count;
+    for (int sidx = 0; sidx < a.nseg; ++sidx) {
+        const SplitSeg g = a.seg[sidx];
+        const int q4 = g.Kout >> 2;
+        const long long total = (long long)cnt * q4;
+        for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+            const int i = (int)(e / q4), k = (int)(e % q4) * 4;
+            const int r = a.rows[i];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < g.K) v = *reinterpret_cast<const float4*>(g.src + (size_t)r * g.ld + k);
+            const float x[4] = {v.x, v.y, v.z, v.w};
+            __half hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                hi[j] = __float2half_rn(x[j]);
+                lo[j] = __float2half_rn((x[j] - __half2float(hi[j])) * 2048.f);
+            }
+            __half2* ph = reinterpret_cast<__half2*>(g.hi + (size_t)i * g.pitch + g.col0 + k);
+            __half2* pl = reinterpret_cast<__half2*>(g.lo + (size_t)i * g.pitch + g.col0 + k);
+            ph[0] = __halves2half2(hi[0], hi[1]); ph[1] = __halves2half2(hi[2], hi[3]);
+            pl[0] = __halves2half2(lo[0], lo[1]); pl[1] = __halves2half2(lo[2], lo[3]);
+        }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -493,6 +548,22 @@ void rc_tc_split_host(const float* w, size_t n, std::vector<uint16_t>& hi, std::
         hi[i] = *reinterpret_cast<const uint16_t*>(&h);
         lo[i] = *reinterpret_cast<const uint16_t*>(&l);
     }
+}
+
+int rc_tc_split_pass(const RcSplitSeg* segs, int nseg, const int* rows, const int* count, int B, void* stream) {
+    SplitPassArgs a;
+    memset(&a, 0, sizeof(a));
+    long long work = 0;
+    for (int i = 0; i < nseg && i < 3; ++i) {
+        a.seg[i].src = segs[i].src; a.seg[i].ld = segs[i].ld; a.seg[i].K = segs[i].K; a.seg[i].Kout = segs[i].Kout; a.seg[i].col0 = segs[i].col0;
+        a.seg[i].pitch = segs[i].pitch; a.seg[i].hi = (__half*)segs[i].hi; a.seg[i].lo = (__half*)segs[i].lo;
+        work = std::max(work, (long long)B * (segs[i].Kout / 4));
+    }
+    a.nseg = nseg; a.rows = rows; a.count = count;
+    const int grid = (int)std::min<long long>(rc_cdiv(work, 256), 148 * 8);
+    RC_LAUNCH(rc_split_pass_kernel, grid, 256, 0, stream, a);
+    RC_CHECK_LAUNCH();
+    return RC_OK;
 }
 
 int rc_tc_split_rows(const float* X, int ldx, const float* X2, int ldx2, int K1, int K2, int Kout, const int* rows, const int* count,
@@ -551,10 +622,12 @@ int rc_tc_lstm_layer_cluster(const RcTensorMap* mAhi, const RcTensorMap* mAlo, c
 }
 
 int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
-                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream) {
+                     const float* bias, float* C, float* Hout, int H, const int* rows, const int* count, int B, void* stream,
+                     void* nAhi, void* nAlo, int npitch) {
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.bias = bias; a.C = C; a.Hout = Hout; a.rows = rows; a.count = count; a.H = H; a.K = 2 * H;
+    a.nAhi = (__half*)nAhi; a.nAlo = (__half*)nAlo; a.npitch = npitch;
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("RC_TC_DBG"); dbg = e ? atoi(e) : 0; }
     a.dbg = dbg;
@@ -563,9 +636,11 @@ int rc_tc_lstm_layer(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcT
 }
 
 int rc_tc_linear(const RcTensorMap* mAhi, const RcTensorMap* mAlo, const RcTensorMap* mWhi, const RcTensorMap* mWlo,
-                 const float* bias, float* Y, int ldy, int N, int K, int relu, const int* rows, const int* count, int B, void* stream) {
+                 const float* bias, float* Y, int ldy, int N, int K, int relu, const int* rows, const int* count, int B, void* stream,
+                 void* nAhi, void* nAlo, int npitch) {
     TcArgs a;
     memset(&a, 0, sizeof(a));
     a.bias = bias; a.Y = Y; a.ldy = ldy; a.N = N; a.relu = relu; a.rows = rows; a.count = count; a.K = K;
+    a.nAhi = (__half*)nAhi; a.nAlo = (__half*)nAlo; a.npitch = npitch;
     return launch_tc<RC_TC_BN, 3, false>(mAhi, mAlo, mWhi, mWlo, a, N, B, stream);
 }

@@ -57,11 +57,13 @@ struct rc_state {
     float *I1 = nullptr, *I2 = nullptr, *I3 = nullptr;
     float *rcr = nullptr, *conf = nullptr, *lerpw = nullptr, *gravity = nullptr;
     // split activations (tensor-core path), one set per concurrent lane: [lane][Bpad, 2*Hmax]
-    uint16_t *Ahi[2] = {nullptr, nullptr}, *Alo[2] = {nullptr, nullptr};
-    RcTensorMap mAhi[2][NNETS], mAlo[2][NNETS];    // A operand as [Bpad, 2H]  (LSTM layers)
-    RcTensorMap mAhi64[2][NNETS], mAlo64[2][NNETS];  // same with 64-row boxes (cluster-multicast kernel)
-    RcTensorMap mA1hi[2][NNETS], mA1lo[2][NNETS];  //              [Bpad, K1p] (linear1)
-    RcTensorMap mA2hi[2][NNETS], mA2lo[2][NNETS];  //              [Bpad, H]   (linear2)
+    // Three operand buffers per lane: buf 0 = linear1 input [Bpad, K1p]; buf 1 = LSTM-0 input [Bpad, 2H], later linear2 input
+    // [Bpad, H]; buf 2 = LSTM-1 input [Bpad, 2H].  Each GEMM epilogue writes its (split) output straight into the next buffer.
+    uint16_t *Ahi[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}}, *Alo[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    RcTensorMap mA0hi[2][NNETS], mA0lo[2][NNETS];  // buf 0 as [Bpad, K1p]
+    RcTensorMap mA1hi[2][NNETS], mA1lo[2][NNETS];  // buf 1 as [Bpad, 2H]
+    RcTensorMap mA1Hhi[2][NNETS], mA1Hlo[2][NNETS];// buf 1 as [Bpad, H]
+    RcTensorMap mA2hi[2][NNETS], mA2lo[2][NNETS];  // buf 2 as [Bpad, 2H]
     // independent sub-net chains (rnn2->rnn3 || rnn4->rnn6, rnn7 || rnn8, late rnn6 || late rnn4) run on two streams
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
