@@ -159,7 +159,7 @@ def test_forward_online_golden(rb, body, golden_dir, case):
 @pytest.mark.parametrize('variant', ['default', 'contact'])
 def test_forward_offline_batched_golden(rb, body, golden_dir, variant, gemm_mode):
     """Batched forward_offline (tiled GEMM kernels, B > 8), ragged lengths, per-row start modes, vs the reference."""
-    cases = [c for c in ONLINE_CASES if c[2] == variant]
+    cases = [c for c in ONLINE_CASES if c[2] == variant and not c[0].startswith('live_')]
     cases = cases * (12 // len(cases) + 1)
     cases = cases[:12]
     gs = [load(golden_dir, 'online_%s.npz' % c[0]) for c in cases]
