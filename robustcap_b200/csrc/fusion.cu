@@ -271,15 +271,11 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
             void* nh = (l == 0) ? (void*)Ah[2] : (Y ? (void*)Ah[1] : nullptr);
             void* nl = (l == 0) ? (void*)Al[2] : (Y ? (void*)Al[1] : nullptr);
             const int np = (l == 0) ? 2 * w.H : w.H;
+            // The GEMM reads the split copies in the operand buffers, never the fp32 state, so the new hidden state goes straight
+            // into h (no scratch + commit launch as in the fp32 paths, where other CTAs still read h_prev while h_new is produced).
             RC_TRY(rc_tc_lstm_layer(l == 0 ? &s->mA1hi[lane][ni] : &s->mA2hi[lane][ni], l == 0 ? &s->mA1lo[lane][ni] : &s->mA2lo[lane][ni],
-                                    &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.hn[l], w.H, rows, count, B, stream, nh, nl, np));
+                                    &w.mWhi[l], &w.mWlo[l], w.bL[l], nb.c[l], nb.h[l], w.H, rows, count, B, stream, nh, nl, np));
             if (prof) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
-        }
-        {
-            const long long work = (long long)B * (w.H / 4);
-            const int grid = (int)std::min<long long>(rc_cdiv(work, 256), 1184);
-            RC_LAUNCH(rc_commit_kernel, grid, 256, 0, stream, nb.hn[0], nb.hn[1], nb.h[0], nb.h[1], w.H, rows, count);
-            RC_CHECK_LAUNCH();
         }
         if (Y) RC_TRY(rc_tc_linear(&s->mA1Hhi[lane][ni], &s->mA1Hlo[lane][ni], &w.mW2hi, &w.mW2lo, w.b2, Y, ldy, w.out, w.H, 0, rows, count, B, stream));
         return RC_OK;
