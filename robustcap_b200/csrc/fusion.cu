@@ -73,13 +73,15 @@ __global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __res
 
 __global__ void __launch_bounds__(128) rc_mid_kernel(const int* __restrict__ flags, int B, const float* __restrict__ rcr,
                                                       const float* __restrict__ lerpw, const float* X3, const float* X6, float* X7) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;           // one thread per (stream, joint)
+    const int b = e / 23, i = e % 23;
     if (b >= B) return;
     const int f = flags[b];
     if (!(f & RC_F_ACTIVE)) return;
     float r[9];
-    for (int i = 0; i < 9; ++i) r[i] = rcr[b * 9 + i];
-    rc_mid_row(f, r, lerpw + b * 2, X3 + (size_t)b * RC_K3 + 72, X6 + (size_t)b * RC_K6 + 171, X7 + (size_t)b * RC_K7 + 72);
+    for (int q = 0; q < 9; ++q) r[q] = rcr[b * 9 + q];
+    rc_mid_joint(f, r, lerpw + b * 2, X3 + (size_t)b * RC_K3 + 72 + i * 3, X6 + (size_t)b * RC_K6 + 171 + i * 3,
+                 X7 + (size_t)b * RC_K7 + 72 + i * 3);
 }
 
 __global__ void __launch_bounds__(64) rc_kin_kernel(RcNetCfg cfg, const RcModelConst* __restrict__ M, RcRowState* rows,
@@ -120,7 +122,7 @@ constexpr int kRowWarps = 4;
 
 __global__ void __launch_bounds__(kRowWarps * 32) rc_prep_warp_kernel(RcNetCfg cfg, const RcRowState* __restrict__ rows, StepIO io, int B,
                                                                        float* X2, float* X3, float* X4, float* X6, float* X7,
-                                                                       float* rcr, float* conf, float* lerpw, int* flags) {
+                                                                       float* rcr, float* conf, float* lerpw, int* flags, int* lists, int* counts) {
     __shared__ RcPrepWarpSmem S[kRowWarps];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kRowWarps + w;
@@ -130,13 +132,20 @@ __global__ void __launch_bounds__(kRowWarps * 32) rc_prep_warp_kernel(RcNetCfg c
     if (io.row_flags && (io.first_mode == 1 || (io.first_mode == 2 && t == 0))) inflags = io.row_flags[b] & 3;
     if (!io.first_tran) inflags &= ~RC_F_FIRST_TRAN;
     const bool active = !io.lengths || t < io.lengths[b];
-    if (!active) { if (lane == 0) flags[b] = 0; return; }
+    if (!active) {
+        if (lane == 0) { flags[b] = 0; if (B == 1 && lists) for (int l = 0; l < NLISTS; ++l) counts[l] = 0; }
+        return;
+    }
     inflags |= RC_F_ACTIVE;
     const int f = rc_prep_warp(cfg, rows[b].vision_count, S[w], io.j2dc + b * io.sj + (long long)t * 99,
                                io.accc + b * io.sa + (long long)t * 18, io.oric + b * io.so + (long long)t * 54, inflags,
                                X2 + (size_t)b * RC_K2, X3 + (size_t)b * RC_K3, X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6,
                                X7 + (size_t)b * RC_K7, rcr + b * 9, conf + b, lerpw + b * 2, lane);
     if (lane == 0) flags[b] = f;
+    if (B == 1 && lane == 0 && lists) {        // single stream: the row lists are trivial, no separate compaction launch
+        const int on[NLISTS] = {1, (f & RC_F_HI) != 0, (f & RC_F_FIRST_FRAME) != 0, (f & RC_F_R6B) != 0, (f & RC_F_LATE) != 0, 0};
+        for (int l = 0; l < NLISTS; ++l) { lists[l] = 0; counts[l] = on[l]; }
+    }
 }
 
 __global__ void __launch_bounds__(kRowWarps * 32) rc_kin_warp_kernel(RcNetCfg cfg, const RcModelConst* __restrict__ M, RcRowState* rows,
@@ -296,7 +305,8 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
         RC_TRY(launch_linear(a, B, true, stream));
         if (prof) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     }
-    {
+    const bool fuse_commit = Y && B <= 8;          // the GEMV linear2 launch also commits h <- h_new (it only reads the scratch)
+    if (!fuse_commit) {
         const long long work = (long long)B * (w.H / 4);
         const int grid = (int)std::min<long long>(rc_cdiv(work, 256), 1184);
         RC_LAUNCH(rc_commit_kernel, grid, 256, 0, stream, nb.hn[0], nb.hn[1], nb.h[0], nb.h[1], w.H, rows, count);
@@ -305,6 +315,7 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
     if (Y) {
         a.X = nb.hn[1]; a.ldx = w.H; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.H; a.K2 = 0;
         a.W = w.W2; a.bias = w.b2; a.N = w.out; a.Nw = w.out4; a.Y = Y; a.ldy = ldy; a.relu = 0; a.C = nullptr; a.Hout = nullptr;
+        if (fuse_commit) { a.commit_src[0] = nb.hn[0]; a.commit_src[1] = nb.hn[1]; a.commit_dst[0] = nb.h[0]; a.commit_dst[1] = nb.h[1]; a.commit_H = w.H; }
         RC_TRY(launch_linear(a, B, false, stream));
     }
     return RC_OK;
@@ -341,10 +352,12 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
                   s->rcr, s->conf, s->lerpw, s->flags);
     else
         RC_LAUNCH(rc_prep_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4,
-                  s->X6, s->X7, s->rcr, s->conf, s->lerpw, s->flags);
+                  s->X6, s->X7, s->rcr, s->conf, s->lerpw, s->flags, s->lists, s->counts);
     RC_CHECK_LAUNCH();
-    RC_LAUNCH(rc_lists_kernel, 1, NLISTS * 32, 0, stream, s->flags, B, s->lists, s->counts);
-    RC_CHECK_LAUNCH();
+    if (B > 1 || scalar_rows) {
+        RC_LAUNCH(rc_lists_kernel, 1, NLISTS * 32, 0, stream, s->flags, B, s->lists, s->counts);
+        RC_CHECK_LAUNCH();
+    }
     // fork/join helpers: the side stream runs the chain that is independent of the main one (both inside the same graph when captured)
     static const bool serial = getenv("RC_SERIAL") != nullptr;               // validation switch: single stream
     cudaStream_t ms = (cudaStream_t)stream;
@@ -359,7 +372,7 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
     if (any_first_frame) RC_TRY(net_pass(s, NET6, L_6A, s->X6, s->Y6, 4, side, sl));   // pc on first_frame (:156)
     RC_TRY(net_pass(s, NET6, L_6B, s->X6, s->Y6, 4, side, sl));                        // pc                (:161,165)
     RC_TRY(join());
-    RC_LAUNCH(rc_mid_kernel, rc_cdiv(B, 128), 128, 0, stream, s->flags, B, s->rcr, s->lerpw, s->X3, s->X6, s->X7);
+    RC_LAUNCH(rc_mid_kernel, rc_cdiv((long long)B * 23, 128), 128, 0, stream, s->flags, B, s->rcr, s->lerpw, s->X3, s->X6, s->X7);
     RC_CHECK_LAUNCH();
     RC_TRY(fork());
     RC_TRY(net_pass(s, NET7, L_ALL, s->X7, s->Y7, 144, stream, 0));                    // poseg6d           (:169)

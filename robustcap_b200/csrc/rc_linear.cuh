@@ -30,6 +30,8 @@ struct RcLinear {
     const int* rows;               // row list
     const int* count;              // device count of valid list entries
     int relu;
+    // optional (GEMV linear2 launch): h <- h_new of both LSTM layers for the rows of the list, so no separate commit launch
+    const float* commit_src[2]; float* commit_dst[2]; int commit_H;
 };
 
 __device__ __forceinline__ float4 rc_ldg_stream(const float* p) {
@@ -70,6 +72,13 @@ __device__ __forceinline__ void rc_gemv_vblock(const RcLinear& a, int ksplit, in
     for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int m = 0; m < M; ++m) acc[r][m] = 0.f;
+    // the finalising lane fetches its cell state now, so the load overlaps the weight stream instead of following it
+    float cprev = 0.f;
+    const bool fin = (ks == 0 && job < njobs && lane < cnt);
+    if (LSTM && fin) {
+        const size_t cidx = (size_t)a.rows[lane] * a.H + job;
+        cprev = COHERENT ? __ldcg(a.C + cidx) : a.C[cidx];
+    }
 
     if (job < njobs) {
         const float* w0 = a.W + (size_t)(job * 4) * K;
@@ -126,7 +135,6 @@ __device__ __forceinline__ void rc_gemv_vblock(const RcLinear& a, int ksplit, in
             const float4 b = *reinterpret_cast<const float4*>(a.bias + job * 4);
             const size_t idx = (size_t)row * a.H + job;
             float cn, hn;
-            const float cprev = COHERENT ? __ldcg(a.C + idx) : a.C[idx];
             rc_lstm_cell(tot[0] + b.x, tot[1] + b.y, tot[2] + b.z, tot[3] + b.w, cprev, cn, hn);
             a.C[idx] = cn;
             a.Hout[idx] = hn;
@@ -150,6 +158,14 @@ __global__ void __launch_bounds__(256) rc_gemv_kernel(RcLinear a, int ksplit) {
     const int cnt = min(*a.count, M);
     if (cnt == 0) return;
     rc_gemv_vblock<M, LSTM, false>(a, ksplit, blockIdx.x, threadIdx.x >> 5, threadIdx.x & 31, part, cnt, 0);
+    if (!LSTM && a.commit_H) {
+        const int q4 = a.commit_H >> 2;
+        for (int e = blockIdx.x * 256 + threadIdx.x; e < cnt * 2 * q4; e += gridDim.x * 256) {
+            const int m = e / (2 * q4), l = (e / q4) & 1, k = (e % q4) * 4;
+            const size_t o = (size_t)a.rows[m] * a.commit_H + k;
+            *reinterpret_cast<float4*>(a.commit_dst[l] + o) = *reinterpret_cast<const float4*>(a.commit_src[l] + o);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -143,18 +143,19 @@ RC_HD int rc_prep_row(const RcNetCfg& cfg, const RcRowState& st, const float* j2
 
 // ---- mid ----------------------------------------------------------------------------------------------------
 // x3 + 72 holds j3dr_i (rnn2 out), x6 + 171 holds j3dc (rnn4 out, camera frame).  Writes j3dr into x7 + 72.
+RC_HD void rc_mid_joint(int flags, const float* rcr, const float* lerpw, const float* j3dr_i, const float* j3dc, float* j3dr) {
+    float v[3];
+    if (flags & (RC_F_GE | RC_F_MID)) rc_vec_mat3(j3dc, rcr, v);                          // j3dc.view(23,3).mm(Rcr) (:154)
+    for (int j = 0; j < 3; ++j) {
+        const float a = j3dr_i[j];
+        if (flags & RC_F_GE) j3dr[j] = v[j];
+        else if (flags & RC_F_MID) j3dr[j] = RC_ADD(RC_MUL(a, lerpw[0]), RC_MUL(v[j], lerpw[1]));     // lerp (:164)
+        else j3dr[j] = a;
+    }
+}
 RC_HD void rc_mid_row(int flags, const float* rcr, const float* lerpw, const float* j3dr_i, const float* j3dc,
                       float* j3dr) {
-    for (int i = 0; i < 23; ++i) {
-        float v[3];
-        if (flags & (RC_F_GE | RC_F_MID)) rc_vec_mat3(j3dc + i * 3, rcr, v);          // j3dc.view(23,3).mm(Rcr) (:154)
-        for (int j = 0; j < 3; ++j) {
-            float a = j3dr_i[i * 3 + j];
-            if (flags & RC_F_GE) j3dr[i * 3 + j] = v[j];
-            else if (flags & RC_F_MID) j3dr[i * 3 + j] = RC_ADD(RC_MUL(a, lerpw[0]), RC_MUL(v[j], lerpw[1]));  // lerp (:164)
-            else j3dr[i * 3 + j] = a;
-        }
-    }
+    for (int i = 0; i < 23; ++i) rc_mid_joint(flags, rcr, lerpw, j3dr_i + i * 3, j3dc + i * 3, j3dr + i * 3);
 }
 
 // ---- kin ----------------------------------------------------------------------------------------------------
