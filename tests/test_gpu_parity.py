@@ -356,3 +356,28 @@ torch.save(out, sys.argv[1])
         assert torch.equal(outs['stream'][name][0], outs['multi'][name][0]), name
         assert torch.equal(outs['stream'][name][1], outs['multi'][name][1]), name
         assert pose_angle(outs['stream'][name][0], g['pose']).max().item() < RAD_TOL
+
+
+def test_ragged_and_degenerate_batches(rb, body, golden_dir):
+    """Edge cases of the batched entry point: zero-length rows, one-frame rows, T = 1, batch sizes on both sides of the GEMV / GEMM
+    switch (8 | 9) and a batch that is not a multiple of the 128-row tile; every row must equal the same sequence run alone."""
+    g = load(golden_dir, 'online_contact_mixed_ft.npz')
+    net = get_net(rb, body, 0, 'contact')
+    rb.Net.gravityc = g['gravity'].clone()
+    T = 12
+    ft = torch.tensor([0., 0., 4.])
+    alone_p, alone_t = net.forward_offline(g['j2dc'][:T].cuda(), g['accc'][:T].cuda(), g['oric'][:T].cuda(), first_tran=ft)
+    for B in (8, 9, 131):
+        lengths = torch.tensor([(i * 5) % (T + 1) for i in range(B)], dtype=torch.int32)       # includes 0, 1 and T
+        j = g['j2dc'][:T].unsqueeze(0).repeat(B, 1, 1, 1).cuda()
+        a = g['accc'][:T].unsqueeze(0).repeat(B, 1, 1, 1).cuda()
+        o = g['oric'][:T].unsqueeze(0).repeat(B, 1, 1, 1, 1).cuda()
+        p, t = net.forward_offline(j, a, o, first_tran=ft, lengths=lengths)
+        for b in range(B):
+            L = int(lengths[b])
+            if L:
+                assert pose_angle(p[b, :L].cpu(), alone_p[:L].cpu()).max().item() < RAD_TOL
+                assert (t[b, :L] - alone_t[:L]).abs().max().item() < POS_TOL
+            assert p[b, L:].abs().max().item() == 0 if L < T else True
+    p1, t1 = net.forward_offline(g['j2dc'][:1].cuda(), g['accc'][:1].cuda(), g['oric'][:1].cuda(), first_tran=ft)
+    assert torch.equal(p1, alone_p[:1]) and torch.equal(t1[0].cpu(), ft)
