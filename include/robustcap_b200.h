@@ -178,6 +178,15 @@ int rc_smplify_loss_grad(rc_smplify* s, const float* d_pose, const float* d_tran
                          const float* d_cam_k, const float* d_ref3d, const float* d_imu_aa, int rodrigues, float* d_loss,
                          float* d_grad_pose, float* d_grad_tran, float* d_reproj, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Evaluation metrics next to the hot path — evaluate.py:120-133 (cal_mpjpe) with utils.py:138-203 (Procrustes).
+ *   d_jreg [nj_rows >= 14, nv] dense joint regressor (J_regressor_h36m), d_pose / d_gt_pose [b,24,3,3] local rotations.
+ *   d_out [b,3] per frame: mean distance of the first 14 regressed joints after pelvis alignment, mean vertex distance,
+ *   Procrustes-aligned mean joint distance (0 when with_pa == 0).  The caller averages over frames like the reference.
+ * ------------------------------------------------------------------------------------------------------- */
+int rc_metrics_mpjpe(const rc_model* m, const float* d_jreg, int32_t nj_rows, const float* d_pose, const float* d_gt_pose,
+                     int64_t b, int with_pa, float* d_out, void* stream);
+
 /* Test tap: one fused LSTM layer of sub-net `ni` (0..5 = rnn2,3,4,6,7,8), layer 0/1, on caller-provided device data for
  * all b rows of the state: d_x [b,H], d_hprev [b,H], d_c [b,H] (in place), d_hout [b,H]; mode as rc_net_set_gemm_mode. */
 int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* d_x, const float* d_hprev, float* d_c,

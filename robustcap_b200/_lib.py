@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO_PATH = os.path.join(CSRC, 'librobustcap_b200.so')
-SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'stream.cu']
+SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'stream.cu', 'metrics.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -104,6 +104,7 @@ _SIGS = {
     'rc_smplify_create': (i32, [ctypes.POINTER(vp), vp, vp, vp, vp, i32]),
     'rc_smplify_destroy': (None, [vp]),
     'rc_smplify_loss_grad': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'rc_metrics_mpjpe': (i32, [vp, vp, i32, vp, vp, i64, i32, vp, vp]),
     'rc_profile_enable': (i32, [vp, i32]),
     'rc_profile_collect': (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]),
 }

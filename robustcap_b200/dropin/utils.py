@@ -12,3 +12,6 @@ def sync_mp3d_from_smpl(vert, joint):
     syn_3d[:, 25:27] = joint[:, 4:6].clone()
     syn_3d[:, 27:29] = joint[:, 7:9].clone()
     return syn_3d
+
+
+from robustcap_b200.metrics import reconstruction_error  # noqa: E402,F401  (utils.py:195-203, used by evaluate.cal_mpjpe)

@@ -260,11 +260,38 @@ def gen_smplify(ref, out):
         print('smplify', name, 'loss_init', float(loss), 'moved', float((po.reshape(T, 24, 3, 3) - pose).abs().max()))
 
 
+def gen_metrics(ref, out):
+    """evaluate.py:120-133 (cal_mpjpe) on seeded random poses — the step right after the hot path."""
+    import evaluate
+    g = torch.Generator().manual_seed(41)
+    T = 9
+    gt = synthetic._random_rotations(T * 24, g).view(T, 24, 3, 3)
+    # prediction = ground truth perturbed by small random rotations (+ one frame with a large error)
+    noise = art_noise(T * 24, g, 0.15).view(T, 24, 3, 3)
+    pose = gt @ noise
+    pose[3] = synthetic._random_rotations(24, g)
+    with torch.no_grad():
+        r3 = evaluate.cal_mpjpe(pose, gt, cal_pampjpe=True)
+        r2 = evaluate.cal_mpjpe(pose, gt)
+    np.savez_compressed(os.path.join(out, 'metrics.npz'), pose=pose.numpy(), gt_pose=gt.numpy(), with_pa=r3.numpy(), without_pa=r2.numpy(),
+                        j_regressor=evaluate.J_regressor.numpy())
+    print('metrics', r3)
+
+
+def art_noise(n, g, scale):
+    aa = torch.randn(n, 3, generator=g) * scale
+    ang = aa.norm(dim=1, keepdim=True)
+    ax = aa / ang
+    K = torch.zeros(n, 3, 3)
+    K[:, 0, 1], K[:, 0, 2], K[:, 1, 0], K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 2], ax[:, 1], ax[:, 2], -ax[:, 0], -ax[:, 1], ax[:, 0]
+    return torch.eye(3) + torch.sin(ang).unsqueeze(-1) * K + (1 - torch.cos(ang)).unsqueeze(-1) * (K @ K)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref = import_reference()
-    which = sys.argv[1:] or ['math', 'kinematics', 'online', 'smplify']
+    which = sys.argv[1:] or ['math', 'kinematics', 'online', 'smplify', 'metrics']
     with torch.no_grad():
         if 'math' in which:
             gen_math(ref, HERE)
@@ -274,6 +301,8 @@ def main():
             gen_online(ref, HERE)
     if 'smplify' in which:
         gen_smplify(ref, HERE)
+    if 'metrics' in which:
+        gen_metrics(ref, HERE)
     print('done')
 
 

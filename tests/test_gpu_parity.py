@@ -381,3 +381,17 @@ def test_ragged_and_degenerate_batches(rb, body, golden_dir):
             assert p[b, L:].abs().max().item() == 0 if L < T else True
     p1, t1 = net.forward_offline(g['j2dc'][:1].cuda(), g['accc'][:1].cuda(), g['oric'][:1].cuda(), first_tran=ft)
     assert torch.equal(p1, alone_p[:1]) and torch.equal(t1[0].cpu(), ft)
+
+
+def test_metrics_cal_mpjpe(rb, body, golden_dir):
+    """the fused GPU cal_mpjpe against the reference's evaluate.cal_mpjpe (golden) — 0.01 mm."""
+    from robustcap_b200.metrics import cal_mpjpe
+    g = load(golden_dir, 'metrics.npz')
+    r3 = cal_mpjpe(body, g['j_regressor'], g['pose'], g['gt_pose'], cal_pampjpe=True)
+    r2 = cal_mpjpe(body, g['j_regressor'], g['pose'], g['gt_pose'])
+    print('gpu', r3.tolist(), 'reference', g['with_pa'].tolist())
+    assert r3.shape == (3,) and r2.shape == (2,)
+    assert (r3 - g['with_pa']).abs().max().item() < 1e-5
+    assert (r2 - g['without_pa']).abs().max().item() < 1e-5
+    same = cal_mpjpe(body, g['j_regressor'], g['gt_pose'], g['gt_pose'], cal_pampjpe=True)
+    assert same.abs().max().item() < 1e-6
