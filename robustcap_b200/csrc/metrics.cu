@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kMT) rc_metrics_mesh_kernel(const float* __res
     for (int e = threadIdx.x; e < 2 * kMJ * 3 + 1; e += kMT) {
         float s = 0.f;
         for (int q = 0; q < kMT / 32; ++q) s += red[q][e];
-        if (e == 2 * kMJ * 3) pve[f] = s / (float)nv;
+        if (e == 2 * kMJ * 3) pve[f * 3] = s / (float)nv;          // column 1 of the [b,3] result
         else kp[f * (2 * kMJ * 3) + e] = s;
     }
 }
