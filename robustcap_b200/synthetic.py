@@ -89,19 +89,22 @@ def write_assets(root, seed=0):
     smpl = os.path.join(root, 'models', 'SMPL_male.pkl')
     gmm = os.path.join(root, 'data', 'dataset_work', 'gmm_08.pkl')
     jr = os.path.join(root, 'data', 'dataset_work', 'J_regressor_h36m.npy')
+    tag = '.tmp%d' % os.getpid()       # several ranks may write concurrently: private temp file, atomic rename
     if not os.path.exists(smpl):
-        with open(smpl + '.tmp', 'wb') as f:
+        with open(smpl + tag, 'wb') as f:
             pickle.dump(make_smpl_dict(seed), f, protocol=2)
-        os.replace(smpl + '.tmp', smpl)
+        os.replace(smpl + tag, smpl)
     if not os.path.exists(gmm):
-        with open(gmm + '.tmp', 'wb') as f:
+        with open(gmm + tag, 'wb') as f:
             pickle.dump(make_gmm_dict(seed + 1), f, protocol=2)
-        os.replace(gmm + '.tmp', gmm)
+        os.replace(gmm + tag, gmm)
     if not os.path.exists(jr):
         rs = np.random.RandomState(seed + 2)
         r = rs.uniform(0, 1, (17, NUM_VERTS)) * (rs.uniform(0, 1, (17, NUM_VERTS)) < 0.004)
         r /= r.sum(axis=1, keepdims=True)
-        np.save(jr, r.astype(np.float32))
+        with open(jr + tag, 'wb') as f:
+            np.save(f, r.astype(np.float32))
+        os.replace(jr + tag, jr)
     return {'smpl_file': smpl, 'gmm_dir': os.path.join(root, 'data', 'dataset_work'), 'j_regressor': jr}
 
 
