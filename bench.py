@@ -46,6 +46,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=300)
     ap.add_argument('--conf', default='mixed')
     ap.add_argument('--cpu-frames', type=int, default=240, help='frames of the bounded CPU-baseline sample')
+    ap.add_argument('--gemm-mode', type=int, default=2, help='2 = persistent grouped tcgen05 kernel (default), 1 = tcgen05 per layer, 0 = fp32 SIMT')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-stream-latency', action='store_true')
     return ap.parse_args()
@@ -106,10 +107,10 @@ class ClockSampler:
         return out
 
 
-def dominant_traffic():
+def dominant_traffic(gemm_mode=1):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
     (profiles/r01_tc_traffic.json, written from the .ncu-rep by profiles/extract_traffic.py); None when absent."""
-    path = os.path.join(REPO, 'profiles', 'r01_tc_traffic.json')
+    path = os.path.join(REPO, 'profiles', 'r01_phase_traffic.json' if gemm_mode == 2 else 'r01_tc_traffic.json')
     if os.path.exists(path):
         return json.load(open(path)).get('dram_bytes_per_launch')
     return None
@@ -226,6 +227,7 @@ def main():
         dist.barrier()
     lib = _lib.load()
     net, sd, assets = build_net()
+    net.set_gemm_mode(args.gemm_mode)
     B, T = args.seqs, args.frames
     inp = synthetic.make_inputs(B, T, seed=1000 + rank, conf=args.conf)
     type(net).gravityc = inp['gravity'].clone()
@@ -307,15 +309,22 @@ def main():
         return
 
     pk = peaks()
-    # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
-    dom_flop = fpr.value * 2 * B * T * args.steps
+    if args.gemm_mode == 2:
+        # dominant kernel = the persistent grouped GEMM; its launches of one frame run the whole LSTM stack of every stream once
+        dom_flop = fpr.value * B * T * args.steps
+        kname = ('rc_tc_phase_kernel (persistent grouped tcgen05 GEMM: all linear1 / LSTM / linear2 layers of a phase of the frame in one '
+                 'launch, 3 launches per frame; kind::f16 on split-fp16 operands, 3 MMAs per fp32-accurate product; CUDA events around every launch)')
+    else:
+        # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
+        dom_flop = fpr.value * 2 * B * T * args.steps
+        kname = ('rc_tc_kernel<128,3,LSTM> (rnn4 fused LSTM layer [rows,2560]x[2560,5120]; tcgen05 kind::f16 on split-fp16 operands, '
+                 '3 MMAs per fp32-accurate product; CUDA events on its launch stream while the other lane runs concurrently)')
     dom_tflops = dom_flop / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
-    roofline = {'kernel': 'rc_tc_kernel<128,3,LSTM> (rnn4 fused LSTM layer [rows,2560]x[2560,5120]; tcgen05 kind::f16 on split-fp16 operands, '
-                          '3 MMAs per fp32-accurate product; CUDA events on its launch stream while the other lane runs concurrently)',
+    roofline = {'kernel': kname,
                 'bound': 'tensor',
                 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': dom_tflops / pk['tflops_sustained'], 'peak_source': 'bf16 sustained, of ' + pk['source'],
-                'traffic': dominant_traffic(), 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,
+                'traffic': dominant_traffic(args.gemm_mode), 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,
                 'tensor_pipe_frac': 3 * dom_tflops / pk['tflops_sustained'],   # 3 fp16 MMAs are issued per algorithmic fp32 product
                 'whole_path_tflops': FLOP_PER_FRAME * B * T / (ms_step * 1e-3) / 1e12,
                 'weight_stream_gbs': WEIGHT_BYTES * T / (ms_step * 1e-3) / 1e9}

@@ -203,6 +203,13 @@ int rc_profile_collect(rc_state* s, double* total_ms, int64_t* launches, double*
  * b * width floats (width = 69,3,69,3,144,2). */
 int rc_state_debug_output(rc_state* s, int which, float* h_out, void* stream);
 
+/* Debug tap of the persistent grouped GEMM kernel (gemm mode 2): enable != 0 makes every later launch record, per tile, 16 int64
+ * {cta<<32|job<<16|row block<<8|column tile, clock64 at: grab, dependency met, first MMA, last commit, accumulators seen by the
+ * epilogue, outputs stored, tile published, then finer epilogue stamps}; with h_out != NULL the trace of `phase` (0 rnn4+rnn2, 1 rnn6 on
+ * first-frame rows, 2 rnn6+rnn3+rnn7+rnn8, 3 vision updater) of the last frame is copied (at most max_tiles tiles) and
+ * *ntiles receives the phase's tile bound. */
+int rc_state_debug_phase_trace(rc_state* s, int enable, int phase, long long* h_out, int max_tiles, int* ntiles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO_PATH = os.path.join(CSRC, 'librobustcap_b200.so')
-SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'stream.cu', 'metrics.cu']
+SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'phase_tc.cu', 'stream.cu', 'metrics.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -100,6 +100,7 @@ _SIGS = {
     'rc_forward_sequence': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp]),
     'rc_forward_sequence_host': (i32, [vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
     'rc_state_debug_output': (i32, [vp, i32, vp, vp]),
+    'rc_state_debug_phase_trace': (i32, [vp, i32, i32, vp, i32, vp]),
     'rc_state_debug_lstm': (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     'rc_smplify_create': (i32, [ctypes.POINTER(vp), vp, vp, vp, vp, i32]),
     'rc_smplify_destroy': (None, [vp]),

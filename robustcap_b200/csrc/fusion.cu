@@ -56,17 +56,26 @@ __global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __res
     if (l >= NLISTS) return;
     if (l == L_INIT) { if (lane == 0) counts[L_INIT] = 0; return; }
     int n = 0;
-    for (int b0 = 0; b0 < B; b0 += 32) {
-        const int b = b0 + lane;
-        const int f = (b < B) ? flags[b] : 0;
-        bool p = (f & RC_F_ACTIVE) != 0;
-        if (l == L_HI) p = p && (f & RC_F_HI);
-        else if (l == L_6A) p = p && (f & RC_F_FIRST_FRAME);
-        else if (l == L_6B) p = p && (f & RC_F_R6B);
-        else if (l == L_LATE) p = p && (f & RC_F_LATE);
-        const unsigned m = __ballot_sync(0xffffffffu, p);
-        if (p) lists[l * B + n + __popc(m & ((1u << lane) - 1u))] = b;
-        n += __popc(m);
+    constexpr int U = 8;                                       // flag loads in flight per lane (the loop is latency bound)
+    for (int b0 = 0; b0 < B; b0 += 32 * U) {
+        int f[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * 32 + lane;
+            f[u] = (b < B) ? flags[b] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int b = b0 + u * 32 + lane;
+            bool p = (f[u] & RC_F_ACTIVE) != 0;
+            if (l == L_HI) p = p && (f[u] & RC_F_HI);
+            else if (l == L_6A) p = p && (f[u] & RC_F_FIRST_FRAME);
+            else if (l == L_6B) p = p && (f[u] & RC_F_R6B);
+            else if (l == L_LATE) p = p && (f[u] & RC_F_LATE);
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            if (p) lists[l * B + n + __popc(m & ((1u << lane) - 1u))] = b;
+            n += __popc(m);
+        }
     }
     if (lane == 0) counts[l] = n;
 }
@@ -257,7 +266,7 @@ int net_pass(rc_state* s, int ni, int li, const float* X, float* Y, int ldy, voi
     // linear1 + relu
     a.X = X; a.ldx = w.K1; a.X2 = nullptr; a.ldx2 = 0; a.K1 = w.K1; a.K2 = 0;
     a.W = w.W1; a.bias = w.b1; a.N = w.H; a.Nw = w.H; a.Y = nb.a1; a.ldy = w.H; a.relu = 1; a.H = w.H;
-    const bool tc = s->net->gemm_mode == 1 && s->tc_ready && B > 8;
+    const bool tc = s->net->gemm_mode >= 1 && s->tc_ready && B > 8;
     if (tc) {
         // tensor-core path: one gather/split pre-pass, then lin1 -> LSTM0 -> LSTM1 -> commit -> lin2, every epilogue writing the
         // next GEMM's A operand directly (split fp16 halves, compact row order)
@@ -343,6 +352,108 @@ int init_pass(rc_state* s, void* stream) {
     return RC_OK;
 }
 
+// ---- persistent grouped kernel (gemm mode 2): job lists per phase -------------------------------------------------------------
+struct ChainSpec { int ni, li; float* Y; int ldy; };
+
+int build_phase(rc_state* s, int ph, const ChainSpec* ch, int nch) {
+    const rc_net* net = s->net;
+    const int B = s->B;
+    const long long Bpad = (long long)((B + 127) / 128) * 128;
+    const int MT = (int)(Bpad / 128);
+    RcPhDesc* d = new RcPhDesc();
+    memset(d, 0, sizeof(*d));
+    int idx[4][4];
+    int nj = 0;
+    for (int layer = 0; layer < 4; ++layer)                 // layer-major job order: every chain's linear1 first, linear2 last
+        for (int c = 0; c < nch; ++c) idx[c][layer] = (layer == 3 && !ch[c].Y) ? -1 : nj++;
+    int rc = RC_OK, max_tiles = 0, nseg = 0;
+    if (nj > RC_PH_MAXJOBS || nch * 3 > RC_PH_MAXSEGS) { rc_set_error("build_phase: too many jobs"); rc = RC_ERR_ARG; }
+    auto mk = [&](RcTensorMap* m, const void* base, int K) { if (rc == RC_OK) rc = rc_tc_make_map(m, base, Bpad, K, 128); };
+    for (int c = 0; c < nch && rc == RC_OK; ++c) {
+        const int ni = ch[c].ni;
+        const NetDev& w = net->nets[ni];
+        const NetBuf& nb = s->nb[ni];
+        const int* rows = s->lists + (size_t)ch[c].li * B;
+        const int* count = s->counts + ch[c].li;
+        uint16_t** Ph = s->Phi[ni];
+        uint16_t** Pl = s->Plo[ni];
+        const int H = w.H;
+        for (int layer = 0; layer < 4; ++layer) {
+            if (idx[c][layer] < 0) continue;
+            RcPhJob& j = d->job[idx[c][layer]];
+            j.rows = rows; j.count = count; j.H = H;
+            j.dep = layer ? idx[c][layer - 1] : -1;
+            if (layer == 0) {
+                mk(&j.mAhi, Ph[0], w.K1p); mk(&j.mAlo, Pl[0], w.K1p);
+                j.mWhi = w.mW1hi; j.mWlo = w.mW1lo; j.bias = w.b1; j.N = H; j.relu = 1; j.K = w.K1p;
+                j.nAhi = Ph[1]; j.nAlo = Pl[1]; j.npitch = 2 * H; j.kind = 0; j.nt = H / RC_TC_BN;
+            } else if (layer == 1 || layer == 2) {
+                const int l = layer - 1;
+                mk(&j.mAhi, Ph[layer], 2 * H); mk(&j.mAlo, Pl[layer], 2 * H);
+                j.mWhi = w.mWhi[l]; j.mWlo = w.mWlo[l]; j.bias = w.bL[l]; j.C = nb.c[l]; j.Hout = nb.h[l]; j.N = 4 * H; j.K = 2 * H;
+                if (l == 0) { j.nAhi = Ph[2]; j.nAlo = Pl[2]; j.npitch = 2 * H; }
+                else if (ch[c].Y) { j.nAhi = Ph[3]; j.nAlo = Pl[3]; j.npitch = H; }
+                j.kind = 1; j.nt = 4 * H / RC_TC_BN;
+            } else {
+                mk(&j.mAhi, Ph[3], H); mk(&j.mAlo, Pl[3], H);
+                j.mWhi = w.mW2hi; j.mWlo = w.mW2lo; j.bias = w.b2; j.Y = ch[c].Y; j.ldy = ch[c].ldy; j.N = w.out; j.K = H;
+                j.kind = 0; j.nt = w.outp / RC_TC_BN;
+            }
+            max_tiles += MT * j.nt;
+        }
+        const float* X = ni == NET2 ? s->X2 : ni == NET3 ? s->X3 : ni == NET4 ? s->X4 : ni == NET6 ? s->X6 : s->X7;
+        s->ph_segs[ph][nseg++] = RcSplitSegM{X, w.K1, w.K1, w.K1p, 0, w.K1p, Ph[0], Pl[0], rows, count};
+        s->ph_segs[ph][nseg++] = RcSplitSegM{nb.h[0], H, H, H, H, 2 * H, Ph[1], Pl[1], rows, count};
+        s->ph_segs[ph][nseg++] = RcSplitSegM{nb.h[1], H, H, H, H, 2 * H, Ph[2], Pl[2], rows, count};
+    }
+    d->njobs = nj;
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->d_phase[ph], (size_t)1);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->d_ctl[ph], (size_t)(1 + RC_PH_MAXJOBS * MT));
+    if (rc == RC_OK && cudaMemcpy(s->d_phase[ph], d, sizeof(*d), cudaMemcpyHostToDevice) != cudaSuccess) { rc_set_error("build_phase: upload failed"); rc = RC_ERR_CUDA; }
+    delete d;
+    s->ph_nseg[ph] = nseg; s->ph_max_tiles[ph] = max_tiles; s->ph_MT = MT;
+    return rc;
+}
+
+int build_phases(rc_state* s) {
+    const rc_net* net = s->net;
+    const long long Bpad = (long long)((s->B + 127) / 128) * 128;
+    for (int i = 0; i < NNETS; ++i) {
+        const NetDev& w = net->nets[i];
+        const size_t n[4] = {(size_t)Bpad * w.K1p, (size_t)Bpad * 2 * w.H, (size_t)Bpad * 2 * w.H, (size_t)Bpad * w.H};
+        for (int q = 0; q < 4; ++q) {
+            RC_TRY(dev_alloc(s->allocs, &s->Phi[i][q], n[q]));
+            RC_TRY(dev_alloc(s->allocs, &s->Plo[i][q], n[q]));
+            RC_CUDA(cudaMemset(s->Phi[i][q], 0, n[q] * 2));
+            RC_CUDA(cudaMemset(s->Plo[i][q], 0, n[q] * 2));
+        }
+    }
+    // within a layer the chain with the longest K goes first, so the short tiles fill the tail of the phase
+    const ChainSpec p1[2] = {{NET4, L_HI, s->X6 + 171, RC_K6}, {NET2, L_ALL, s->X3 + 72, RC_K3}};
+    const ChainSpec p6a[1] = {{NET6, L_6A, s->Y6, 4}};
+    const ChainSpec p2[4] = {{NET6, L_6B, s->Y6, 4}, {NET3, L_ALL, s->Y3, 4}, {NET7, L_ALL, s->Y7, 144}, {NET8, L_ALL, s->Y8, 4}};
+    const ChainSpec pl[2] = {{NET4, L_LATE, nullptr, 0}, {NET6, L_LATE, nullptr, 0}};
+    RC_TRY(build_phase(s, PH_1, p1, 2));
+    RC_TRY(build_phase(s, PH_6A, p6a, 1));
+    RC_TRY(build_phase(s, PH_2, p2, 4));
+    RC_TRY(build_phase(s, PH_LATE, pl, 2));
+    s->ph_ready = true;
+    return RC_OK;
+}
+
+int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr) {
+    RC_TRY(rc_tc_split_multi(s->ph_segs[ph], s->ph_nseg[ph], s->B, s->d_ctl[ph], 1 + RC_PH_MAXJOBS * s->ph_MT, stream, advance));
+    if (s->prof_on) {                  // CUDA events right around the grouped GEMM launch, on the stream it is launched on
+        if (s->prof_used + 2 > s->prof_ev.size()) {
+            for (int q = 0; q < 256; ++q) { cudaEvent_t e; RC_CUDA(cudaEventCreate(&e)); s->prof_ev.push_back(e); }
+        }
+        RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
+    }
+    RC_TRY(rc_tc_phase(s->d_phase[ph], s->d_ctl[ph], s->ph_MT, s->ph_max_tiles[ph], stream, s->d_trace[ph]));
+    if (s->prof_on) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
+    return RC_OK;
+}
+
 int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advance, void* stream) {
     const rc_net* n = s->net;
     const int B = s->B;
@@ -357,6 +468,30 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
     if (B > 1 || scalar_rows) {
         RC_LAUNCH(rc_lists_kernel, 1, NLISTS * 32, 0, stream, s->flags, B, s->lists, s->counts);
         RC_CHECK_LAUNCH();
+    }
+    if (n->gemm_mode == 2 && s->ph_ready && B > 8) {
+        // persistent grouped kernel: rnn4 + rnn2 | mid | [rnn6 on first-frame rows] | rnn6 + rnn3 + rnn7 + rnn8 | kin | vision updater
+        // (rnn7 / rnn8 only need the outputs of rnn2 / rnn4 (:169-170), so they share a launch with rnn3 / rnn6)
+        RC_TRY(run_phase(s, PH_1, stream));
+        RC_LAUNCH(rc_mid_kernel, rc_cdiv((long long)B * 23, 128), 128, 0, stream, s->flags, B, s->rcr, s->lerpw, s->X3, s->X6, s->X7);
+        RC_CHECK_LAUNCH();
+        if (any_first_frame) RC_TRY(run_phase(s, PH_6A, stream));
+        RC_TRY(run_phase(s, PH_2, stream));
+        if (scalar_rows)
+            RC_LAUNCH(rc_kin_kernel, rc_cdiv(B, 64), 64, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B, io, s->Y7, s->Y8,
+                      s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
+        else
+            RC_LAUNCH(rc_kin_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B,
+                      io, s->Y7, s->Y8, s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
+        RC_CHECK_LAUNCH();
+        // init_net (re-seeds rnn2, :178-183) touches none of the vision updater's state: side stream.  The frame cursor is advanced by
+        // the updater's pre-pass (prep and kin, its only readers, are done).
+        static const bool serial2 = getenv("RC_SERIAL") != nullptr;
+        if (!serial2) { RC_CUDA(cudaEventRecord(s->ev_fork, (cudaStream_t)stream)); RC_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0)); }
+        RC_TRY(init_pass(s, serial2 ? stream : (void*)s->side));
+        RC_TRY(run_phase(s, PH_LATE, stream, advance ? s->d_t : nullptr));
+        if (!serial2) { RC_CUDA(cudaEventRecord(s->ev_join, s->side)); RC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_join, 0)); }
+        return RC_OK;
     }
     // fork/join helpers: the side stream runs the chain that is independent of the main one (both inside the same graph when captured)
     static const bool serial = getenv("RC_SERIAL") != nullptr;               // validation switch: single stream
@@ -539,8 +674,8 @@ int rc_net_finalize(rc_net* n) {
 int64_t rc_net_weight_bytes(const rc_net* n) { return n ? n->weight_bytes : 0; }
 
 int rc_net_set_gemm_mode(rc_net* n, int mode) {
-    RC_ARG(n && (mode == 0 || mode == 1));
-    if (mode == 1 && !n->tc_ready) { rc_set_error("tensor-core path unavailable (tensor maps could not be created)"); return RC_ERR_STATE; }
+    RC_ARG(n && (mode == 0 || mode == 1 || mode == 2));
+    if (mode >= 1 && !n->tc_ready) { rc_set_error("tensor-core path unavailable (tensor maps could not be created)"); return RC_ERR_STATE; }
     n->gemm_mode = mode;
     return RC_OK;
 }
@@ -585,14 +720,15 @@ int rc_state_create(rc_state** out, const rc_net* net, int32_t B) {
             }
         }
     }
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->flags, (size_t)B);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->lists, (size_t)NLISTS * B);
+    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->counts, (size_t)NLISTS);
+    if (rc == RC_OK && s->tc_ready) rc = build_phases(s);
     if (rc == RC_OK) {
         if (cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming) != cudaSuccess) { rc_set_error("stream/event creation failed"); rc = RC_ERR_CUDA; }
     }
-    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->flags, (size_t)B);
-    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->lists, (size_t)NLISTS * B);
-    if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->counts, (size_t)NLISTS);
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->d_t, (size_t)1);
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->rows, (size_t)B);
     if (rc != RC_OK) { rc_state_destroy(s); return rc; }
@@ -750,7 +886,7 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
         return RC_OK;
     }
     std::vector<const void*> key = {j2dc, accc, oric, lengths, gravity, first_tran, row_flags, pose, tran,
-                                    (const void*)(intptr_t)T, (const void*)stream};
+                                    (const void*)(intptr_t)T, (const void*)stream, (const void*)(intptr_t)s->net->gemm_mode};
     if (!s->graph || key != s->graph_key) {
         if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
         cudaGraph_t g = nullptr;
@@ -858,11 +994,46 @@ int rc_profile_collect(rc_state* s, double* total_ms, int64_t* launches, double*
     }
     *total_ms = tot;
     *launches = (int64_t)(s->prof_used / 2);
-    if (flop_per_row) {                       // one stream-row through one rnn4 LSTM layer: 2 * 4H * 2H
-        const double H = (double)s->net->nets[NET4].H;
-        *flop_per_row = 2.0 * 4.0 * H * 2.0 * H;
+    if (flop_per_row) {
+        if (s->net->gemm_mode == 2 && s->ph_ready && s->B > 8) {
+            // grouped kernel: the launches of one frame together run the whole LSTM stack of one stream once (SURVEY.md 8d:
+            // 60 689 920 MAC = 121.4 MFLOP per stream-frame)
+            double mac = 0;
+            for (int i = 0; i < NNETS; ++i) {
+                const NetDev& w = s->net->nets[i];
+                mac += (double)w.in * w.H + 16.0 * w.H * w.H + (double)w.H * w.out;
+            }
+            *flop_per_row = 2.0 * mac;
+        } else {                              // one stream-row through one rnn4 LSTM layer: 2 * 4H * 2H
+            const double H = (double)s->net->nets[NET4].H;
+            *flop_per_row = 2.0 * 4.0 * H * 2.0 * H;
+        }
     }
     s->prof_used = 0;
+    return RC_OK;
+}
+
+// Debug tap of the persistent grouped kernel: enable != 0 allocates per-phase tile traces (16 x int64 per tile, see rc_phase.cuh) that
+// every later launch overwrites; phase in [0, 4) with out != null copies that phase's trace (up to max_tiles tiles) and returns in
+// *ntiles the upper bound of tiles of the phase.
+int rc_state_debug_phase_trace(rc_state* s, int enable, int phase, long long* out, int max_tiles, int* ntiles) {
+    RC_ARG(s);
+    if (!s->ph_ready) { rc_set_error("grouped kernel not available for this state"); return RC_ERR_STATE; }
+    if (enable) {
+        for (int ph = 0; ph < PH_COUNT; ++ph) {
+            if (s->d_trace[ph]) continue;
+            RC_TRY(dev_alloc(s->allocs, &s->d_trace[ph], (size_t)s->ph_max_tiles[ph] * 16));
+            RC_CUDA(cudaMemset(s->d_trace[ph], 0, (size_t)s->ph_max_tiles[ph] * 128));
+        }
+        if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+    }
+    if (out) {
+        RC_ARG(phase >= 0 && phase < PH_COUNT && s->d_trace[phase]);
+        RC_CUDA(cudaDeviceSynchronize());
+        const int n = std::min(max_tiles, s->ph_max_tiles[phase]);
+        RC_CUDA(cudaMemcpy(out, s->d_trace[phase], (size_t)n * 128, cudaMemcpyDeviceToHost));
+        if (ntiles) *ntiles = s->ph_max_tiles[phase];
+    }
     return RC_OK;
 }
 

@@ -7,6 +7,7 @@
 #include "rc_rows.h"
 #include "rc_model.cuh"
 #include "rc_tc.cuh"
+#include "rc_phase.cuh"
 
 enum { NET2 = 0, NET3, NET4, NET6, NET7, NET8, NNETS };
 static const int kNetId[NNETS] = {2, 3, 4, 6, 7, 8};
@@ -18,6 +19,9 @@ static const int kInitDims[4] = {69, 512, 1024, 2048};
 constexpr int kInitK0 = 80;
 
 enum { L_ALL = 0, L_HI, L_6A, L_6B, L_LATE, L_INIT, NLISTS };
+// phases of a frame for the persistent grouped kernel: rnn4 + rnn2 | rnn6 on first-frame rows | rnn6 + rnn3 + rnn7 + rnn8 |
+// vision updater (rnn4 + rnn6 on the low-confidence rows)
+enum { PH_1 = 0, PH_6A, PH_2, PH_LATE, PH_COUNT };
 
 struct NetDev {
     int in = 0, K1 = 0, H = 0, out = 0, out4 = 0;
@@ -42,7 +46,8 @@ struct rc_net {
     float *Wi[3] = {nullptr, nullptr, nullptr}, *bi[3] = {nullptr, nullptr, nullptr};   // init_net
     int64_t weight_bytes = 0;
     std::vector<void*> allocs;
-    int gemm_mode = 1;          // 0 = fp32 SIMT tiles, 1 = tcgen05 split-fp16 (batches > 8 streams)
+    int gemm_mode = 2;          // 0 = fp32 SIMT tiles, 1 = tcgen05 split-fp16, one launch per layer, 2 = tcgen05 persistent
+                                // grouped kernel, one launch per phase of the frame (batches > 8 streams)
     bool tc_ready = false;
 };
 
@@ -68,6 +73,17 @@ struct rc_state {
     cudaStream_t side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     bool tc_ready = false;
+    // persistent grouped kernel (phase_tc.cu): per-net operand buffers (0 = linear1 input [Bpad,K1p], 1 = LSTM-0 input [Bpad,2H],
+    // 2 = LSTM-1 input [Bpad,2H], 3 = linear2 input [Bpad,H]), one job list + control block + split-segment list per phase
+    uint16_t *Phi[NNETS][4] = {}, *Plo[NNETS][4] = {};
+    RcPhDesc* d_phase[PH_COUNT] = {};
+    int* d_ctl[PH_COUNT] = {};
+    int ph_max_tiles[PH_COUNT] = {};
+    RcSplitSegM ph_segs[PH_COUNT][RC_PH_MAXSEGS];
+    int ph_nseg[PH_COUNT] = {};
+    int ph_MT = 0;
+    long long* d_trace[PH_COUNT] = {};   // debug tile traces (rc_state_debug_phase_trace)
+    bool ph_ready = false;
     int* flags = nullptr;
     int* lists = nullptr;      // [NLISTS][B]
     int* counts = nullptr;     // [NLISTS]

@@ -1,0 +1,44 @@
+// Interface of the persistent grouped tcgen05 kernel (phase_tc.cu): ONE launch executes every GEMM of a "phase" of the frame
+// (the linear1 -> LSTM-0 -> LSTM-1 -> linear2 chains of up to four sub-nets of net/sig_mp.py:126-129 that have no mutual
+// dependencies), tile by tile, with the layer-to-layer dependencies tracked per 128-row block in global memory.
+#pragma once
+#include "rc_tc.cuh"
+
+constexpr int RC_PH_MAXJOBS = 16;
+constexpr int RC_PH_MAXSEGS = 12;
+
+// One GEMM of a phase.  kind 0: Y = act(A W^T + b) (linear1 / linear2); kind 1: fused LSTM layer (gates -> c, h).
+// A is the compact-row split-fp16 operand buffer of the chain ([Bpad, K], 128-row TMA boxes), W the split weights
+// ([N padded to 128, K]).  (nAhi, nAlo, npitch): when set, the outputs are also written as fp16 halves into the NEXT job's
+// A operand.  dep: index of the job (of the same chain) whose 128-row block must be complete before this job may load it.
+struct alignas(64) RcPhJob {
+    RcTensorMap mAhi, mAlo, mWhi, mWlo;
+    const float* bias;
+    float* C;              // LSTM: cell state [*, H], in place
+    float* Hout;           // LSTM: hidden state [*, H]
+    float* Y;              // linear: output rows (may be null)
+    const int* rows;       // row list of the chain
+    const int* count;
+    void* nAhi;
+    void* nAlo;
+    int ldy, N, relu, H, K, npitch;
+    int kind, nt, dep;
+    int pad_[3];
+};
+struct alignas(64) RcPhDesc {
+    int njobs;
+    int pad_[15];
+    RcPhJob job[RC_PH_MAXJOBS];
+};
+
+// d_ctl: [1 + RC_PH_MAXJOBS * MT] ints, all zero at launch (ctl[0] = tile scheduler, then per job and 128-row block the number
+// of finished tiles); MT = row blocks per job at most; max_tiles bounds the grid.
+// d_trace (debug, normally null): per tile 16 x int64 {cta<<32|job<<16|m<<8|n, t_grab, t_dep, t_mma0, t_commit, t_epi0, t_stored, t_done,
+// t_handed_back, then per 32-column chunk (LSTM jobs): t_tmem_read, t_math, t_stores_issued, ...} (clock64 of the SM)
+int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void* stream, long long* d_trace = nullptr);
+
+// Gather + split pre-pass for all chains of a phase in one launch: segment i copies rows rows_i[0..*count_i) of src
+// ([*, ld], first K columns valid, zero up to Kout) into (hi, lo)[compact row * pitch + col0 ...]; also zeroes `zero[0..nzero)`.
+struct RcSplitSegM { const float* src; int ld, K, Kout, col0, pitch; void* hi; void* lo; const int* rows; const int* count; };
+// `advance` (optional): an int the launch increments once (the sequence-mode frame cursor).
+int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance = nullptr);

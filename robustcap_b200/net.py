@@ -136,7 +136,8 @@ class Net(torch.nn.Module):
         return out
 
     def set_gemm_mode(self, mode):
-        """Batched (B > 8) LSTM GEMM back end: 1 = tcgen05 tensor cores on split-fp16 operands (default), 0 = fp32 SIMT."""
+        """Batched (B > 8) GEMM back end: 2 = persistent grouped tcgen05 kernel, one launch per phase of the frame (default),
+        1 = tcgen05 one launch per layer, 0 = fp32 SIMT tiles.  Both tcgen05 paths use split-fp16 operands (fp32-accurate)."""
         self._ensure_native()
         _lib.check(_lib.load().rc_net_set_gemm_mode(self._net, int(mode)))
         self._gemm_mode = int(mode)
