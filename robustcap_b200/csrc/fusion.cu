@@ -359,7 +359,7 @@ int build_phase(rc_state* s, int ph, const ChainSpec* ch, int nch) {
     const rc_net* net = s->net;
     const int B = s->B;
     const long long Bpad = (long long)((B + 127) / 128) * 128;
-    const int MT = (int)(Bpad / 128);
+    const int MT = (int)(Bpad / 128 + 1) / 2 * 2;          // even: the CTA-pair kernel works on pairs of row blocks
     RcPhDesc* d = new RcPhDesc();
     memset(d, 0, sizeof(*d));
     int idx[4][4];
@@ -385,18 +385,18 @@ int build_phase(rc_state* s, int ph, const ChainSpec* ch, int nch) {
             j.dep = layer ? idx[c][layer - 1] : -1;
             if (layer == 0) {
                 mk(&j.mAhi, Ph[0], w.K1p); mk(&j.mAlo, Pl[0], w.K1p);
-                j.mWhi = w.mW1hi; j.mWlo = w.mW1lo; j.bias = w.b1; j.N = H; j.relu = 1; j.K = w.K1p;
+                j.mWhi = w.mW1hi; j.mWlo = w.mW1lo; j.mWhi64 = w.mW1hi64; j.mWlo64 = w.mW1lo64; j.bias = w.b1; j.N = H; j.relu = 1; j.K = w.K1p;
                 j.nAhi = Ph[1]; j.nAlo = Pl[1]; j.npitch = 2 * H; j.kind = 0; j.nt = H / RC_TC_BN;
             } else if (layer == 1 || layer == 2) {
                 const int l = layer - 1;
                 mk(&j.mAhi, Ph[layer], 2 * H); mk(&j.mAlo, Pl[layer], 2 * H);
-                j.mWhi = w.mWhi[l]; j.mWlo = w.mWlo[l]; j.bias = w.bL[l]; j.C = nb.c[l]; j.Hout = nb.h[l]; j.N = 4 * H; j.K = 2 * H;
+                j.mWhi = w.mWhi[l]; j.mWlo = w.mWlo[l]; j.mWhi64 = w.mWhi64[l]; j.mWlo64 = w.mWlo64[l]; j.bias = w.bL[l]; j.C = nb.c[l]; j.Hout = nb.h[l]; j.N = 4 * H; j.K = 2 * H;
                 if (l == 0) { j.nAhi = Ph[2]; j.nAlo = Pl[2]; j.npitch = 2 * H; }
                 else if (ch[c].Y) { j.nAhi = Ph[3]; j.nAlo = Pl[3]; j.npitch = H; }
                 j.kind = 1; j.nt = 4 * H / RC_TC_BN;
             } else {
                 mk(&j.mAhi, Ph[3], H); mk(&j.mAlo, Pl[3], H);
-                j.mWhi = w.mW2hi; j.mWlo = w.mW2lo; j.bias = w.b2; j.Y = ch[c].Y; j.ldy = ch[c].ldy; j.N = w.out; j.K = H;
+                j.mWhi = w.mW2hi; j.mWlo = w.mW2lo; j.mWhi64 = w.mW2hi64; j.mWlo64 = w.mW2lo64; j.bias = w.b2; j.Y = ch[c].Y; j.ldy = ch[c].ldy; j.N = w.out; j.K = H;
                 j.kind = 0; j.nt = w.outp / RC_TC_BN;
             }
             max_tiles += MT * j.nt;
@@ -657,7 +657,9 @@ int rc_net_finalize(rc_net* n) {
         RC_TRY(pack_linear(n, p + ".linear2", d.out, d.H, d.out4, d.H, &d.W2, &d.b2, d.outp, d.H, &d.W2hi, &d.W2lo));
         if (n->tc_ready) {
             if (rc_tc_make_map(&d.mW1hi, d.W1hi, d.H, d.K1p, RC_TC_BN) != RC_OK || rc_tc_make_map(&d.mW1lo, d.W1lo, d.H, d.K1p, RC_TC_BN) != RC_OK ||
-                rc_tc_make_map(&d.mW2hi, d.W2hi, d.outp, d.H, RC_TC_BN) != RC_OK || rc_tc_make_map(&d.mW2lo, d.W2lo, d.outp, d.H, RC_TC_BN) != RC_OK)
+                rc_tc_make_map(&d.mW2hi, d.W2hi, d.outp, d.H, RC_TC_BN) != RC_OK || rc_tc_make_map(&d.mW2lo, d.W2lo, d.outp, d.H, RC_TC_BN) != RC_OK ||
+                rc_tc_make_map(&d.mW1hi64, d.W1hi, d.H, d.K1p, 64) != RC_OK || rc_tc_make_map(&d.mW1lo64, d.W1lo, d.H, d.K1p, 64) != RC_OK ||
+                rc_tc_make_map(&d.mW2hi64, d.W2hi, d.outp, d.H, 64) != RC_OK || rc_tc_make_map(&d.mW2lo64, d.W2lo, d.outp, d.H, 64) != RC_OK)
                 n->tc_ready = false;
         }
     }

@@ -32,6 +32,7 @@ struct NetDev {
     int K1p = 0, outp = 0;                                                   // linear1 K padded to 64, linear2 rows padded to RC_TC_BN
     uint16_t *W1hi = nullptr, *W1lo = nullptr, *W2hi = nullptr, *W2lo = nullptr;
     RcTensorMap mW1hi, mW1lo, mW2hi, mW2lo;
+    RcTensorMap mW1hi64, mW1lo64, mW2hi64, mW2lo64;                          // 64-row boxes (CTA-pair kernel)
 };
 struct NetBuf {
     float *h[2] = {nullptr, nullptr}, *c[2] = {nullptr, nullptr}, *hn[2] = {nullptr, nullptr}, *a1 = nullptr;

@@ -13,6 +13,7 @@ constexpr int RC_PH_MAXSEGS = 12;
 // A operand.  dep: index of the job (of the same chain) whose 128-row block must be complete before this job may load it.
 struct alignas(64) RcPhJob {
     RcTensorMap mAhi, mAlo, mWhi, mWlo;
+    RcTensorMap mWhi64, mWlo64;   // the same weights with 64-row boxes (CTA-pair kernel: each CTA loads half of a W tile)
     const float* bias;
     float* C;              // LSTM: cell state [*, H], in place
     float* Hout;           // LSTM: hidden state [*, H]

@@ -50,12 +50,10 @@ for ph in (0, 2, 3):
         s = job == jj
         f = lambda x: '%7d/%-8d' % (np.median(x[s]), x[s].max())
         print(' %3d %6d | %s %s %s %s %s %s %s' % (jj, s.sum(), f(dep), f(fill), f(mma), f(lag), f(epa), f(epb), f(tot)))
-    e = lambda a, b: '%6d' % np.median(tr[s2, a] - tr[s2, b])
     for jj in np.unique(job):
-        s2 = (job == jj) & (tr[:, 10] != 0)
-        if s2.sum():
-            print('   job %d epilogue: phaseA %s | chunk0: tmem %s math %s stores %s | chunk1: tmem %s math %s stores %s' % (
-                jj, e(8, 5), e(9, 8), e(10, 9), e(11, 10), e(12, 11), e(13, 12), e(14, 13)))
+        s2 = job == jj
+        print('   job %2d MMA thread waits (median cycles): tile descriptor %6d | accumulators handed back %6d | operand stages (sum over K blocks) %6d of %6d issue time' % (
+            jj, np.median(tr[s2, 9]), np.median(tr[s2, 10]), np.median(tr[s2, 11]), np.median(mma[s2])))
     # per-CTA span and busy fraction
     spans, busy = [], []
     for c in np.unique(cta):
