@@ -12,7 +12,7 @@ NCCL gather of pose/tran to rank 0, inside the timed region.
 
   value  frames/s, whole job, inputs already resident in HBM (device-timed with CUDA events, max over ranks)
   e2e    the same pass through the host-buffer C-ABI entry point (pinned host inputs -> H2D -> kernels -> D2H)
-  roofline       dominant kernel = rnn4's fused LSTM-layer GEMM ([rows,2560] x [2560,5120] fp32), CUDA-event timed
+  roofline       dominant kernel = the persistent grouped tcgen05 GEMM (3 launches per frame run the whole LSTM stack), CUDA-event timed
   cpu_baseline   the oracle port of the reference loop on the host cores, bounded sample
 """
 import argparse
@@ -312,8 +312,9 @@ def main():
     if args.gemm_mode == 2:
         # dominant kernel = the persistent grouped GEMM; its launches of one frame run the whole LSTM stack of every stream once
         dom_flop = fpr.value * B * T * args.steps
-        kname = ('rc_tc_phase_kernel (persistent grouped tcgen05 GEMM: all linear1 / LSTM / linear2 layers of a phase of the frame in one '
-                 'launch, 3 launches per frame; kind::f16 on split-fp16 operands, 3 MMAs per fp32-accurate product; CUDA events around every launch)')
+        kname = ('rc_tc_phase_pair_kernel (persistent grouped tcgen05 GEMM on CTA pairs, cta_group::2 M=256: all linear1 / LSTM / linear2 '
+                 'layers of a phase of the frame in one launch, 3 launches per frame; kind::f16 on split-fp16 operands, 3 MMAs per '
+                 'fp32-accurate product; CUDA events around every launch)')
     else:
         # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
         dom_flop = fpr.value * 2 * B * T * args.steps
