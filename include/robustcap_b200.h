@@ -111,8 +111,9 @@ int rc_net_set_config(rc_net* n, const rc_net_config* cfg);
 int rc_net_set_tensor(rc_net* n, const char* key, const float* h_data, int64_t numel);
 int rc_net_finalize(rc_net* n);
 int64_t rc_net_weight_bytes(const rc_net* n);     /* bytes of packed per-frame weights resident in HBM */
-/* Batched (B > 8) LSTM-layer GEMM back end: 1 (default) = tcgen05 tensor cores on split-fp16 operands with fp32-level
- * accuracy (gemm_tc.cu), 0 = fp32 SIMT tiles.  B <= 8 always uses the weight-streaming GEMV kernels. */
+/* Batched (B > 8) GEMM back end: 2 (default) = persistent grouped tcgen05 kernel on CTA pairs, one launch per phase of the frame
+ * (phase_tc.cu); 1 = tcgen05, one launch per layer (gemm_tc.cu); 0 = fp32 SIMT tiles.  Both tcgen05 paths use split-fp16
+ * operands with fp32-level accuracy.  B <= 8 always uses the weight-streaming GEMV kernels. */
 int rc_net_set_gemm_mode(rc_net* n, int mode);
 
 int rc_state_create(rc_state** out, const rc_net* net, int32_t b);
@@ -191,6 +192,28 @@ int rc_metrics_mpjpe(const rc_model* m, const float* d_jreg, int32_t nj_rows, co
  * all b rows of the state: d_x [b,H], d_hprev [b,H], d_c [b,H] (in place), d_hout [b,H]; mode as rc_net_set_gemm_mode. */
 int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* d_x, const float* d_hprev, float* d_c,
                         float* d_hout, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Callers / data formats on either side of the hot path.
+ * ------------------------------------------------------------------------------------------------------- */
+/* evaluate.py:38-52, 68-73 — dataset rows -> network inputs, packed on the device.  Row b (one sequence seen by one camera)
+ * has row_off[b+1] - row_off[b] frames; its key points d_j2d [sum, 33, 3] are (u, v, confidence) with u, v in [0, 1]
+ * (scaled by img_w, img_h to pixels); the world-frame IMU arrays d_imu_acc [*, 6, 3] / d_imu_ori [*, 6, 3, 3] are indexed through
+ * d_src[b] (source sequence) and d_seq_off (int64 frame offsets), so the cameras of a sequence share them.  d_cam_T [B,4,4] is
+ * Tcw, d_cam_K [B,3,3] the intrinsics.  Outputs: d_j2dc [B,Tmax,33,3] = (K^-1 [u w, v h, 1])_xy with the confidence,
+ * d_accc = R acc, d_oric = R ori (zeros / identity beyond the row's length), d_gravity [B,3] = R [0,-1,0], d_lengths int32 [B]. */
+int rc_pack_inputs(int32_t b, int32_t t_max, const int32_t* d_src, const int64_t* d_seq_off, const int64_t* d_row_off,
+                   const float* d_j2d, const float* d_imu_acc, const float* d_imu_ori, const float* d_cam_T, const float* d_cam_K,
+                   float img_w, float img_h, float* d_j2dc, float* d_accc, float* d_oric, float* d_gravity, int32_t* d_lengths,
+                   void* stream);
+/* preprocess.py:22-33, 290-302 — synthetic IMU readings of a pose sequence: mesh FK restricted to the n_imu vertices h_vi
+ * (config.vi_mask), accelerations by _syn_acc (second differences at 60 fps, smoothed over +-smooth_n frames; smooth_n = 2 in the
+ * reference), orientations = global rotations of the joints h_ji (config.ji_mask).  d_pose [n,24,3,3] local rotations, d_tran [n,3]
+ * or NULL, d_joints_rest [n,24,3] / d_imu_vrest [n_imu,3] zero-pose joints / IMU vertices of a shaped body or NULL (mean shape).
+ * Outputs d_acc [n,n_imu,3], d_ori [n,n_imu,3,3]; optional d_joint [n,24,3], d_vimu [n,n_imu,3]. */
+int rc_synthesize_imu(const rc_model* m, const float* d_pose, const float* d_tran, const float* d_joints_rest,
+                      const float* d_imu_vrest, const int32_t* h_vi, const int32_t* h_ji, int32_t n_imu, int32_t smooth_n, int64_t n,
+                      float* d_acc, float* d_ori, float* d_joint, float* d_vimu, void* stream);
 
 /* CUDA-event timing of the dominant kernel (the fused LSTM layers of rnn4: [rows, 2H] x [2H, 4H], H = 1280) for
  * bench.py's roofline: enable, run (non-graph launches), collect.  collect synchronises the device, returns the

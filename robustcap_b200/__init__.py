@@ -6,6 +6,8 @@ Public surface mirrors the reference (shaohua-pan/RobustCap):
   robustcap_b200.RNN / RNNWithInit
   robustcap_b200.Net             == net.sig_mp.Net (+ forward_offline)
   robustcap_b200.smplify_runner  == net.smplify.run.smplify_runner
+  robustcap_b200.pipeline        dataset rows -> packed device batch (evaluate.py:24-73), IMU synthesis (preprocess.py:22-33)
+  robustcap_b200.metrics         cal_mpjpe on the device (evaluate.py:120-133)
 Drop-in module names (``articulate``, ``net.sig_mp``, ``net.smplify.run``, ``config``, ``utils``) live in
 ``robustcap_b200/dropin`` — put that directory first on ``sys.path``.
 """

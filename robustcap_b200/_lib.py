@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO_PATH = os.path.join(CSRC, 'librobustcap_b200.so')
-SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'phase_tc.cu', 'stream.cu', 'metrics.cu']
+SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'phase_tc.cu', 'stream.cu', 'metrics.cu', 'pipeline.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -106,6 +106,8 @@ _SIGS = {
     'rc_smplify_destroy': (None, [vp]),
     'rc_smplify_loss_grad': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
     'rc_metrics_mpjpe': (i32, [vp, vp, i32, vp, vp, i64, i32, vp, vp]),
+    'rc_pack_inputs': (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]),
+    'rc_synthesize_imu': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, vp, vp]),
     'rc_profile_enable': (i32, [vp, i32]),
     'rc_profile_collect': (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]),
 }

@@ -190,6 +190,13 @@ int rc_smpl_chain_launch(const rc_model* m, const float* pose, long long b, floa
     return RC_OK;
 }
 
+int rc_smpl_chain_launch_ex(const rc_model* m, const float* pose, const float* tran, const float* jrest_b, long long b, float* Rg,
+                            float* joint, float* Tskin, void* stream) {
+    RC_LAUNCH(rc_smpl_chain_kernel, rc_cdiv(b, kChainFrames), 32, 0, stream, m->d_const, pose, tran, jrest_b, b, Rg, joint, Tskin);
+    RC_CHECK_LAUNCH();
+    return RC_OK;
+}
+
 extern "C" {
 
 int rc_tree_fk_R(const float* i, float* o, const int32_t* p, int nj, int64_t b, void* s) { return run_tree<FK_R>(i, o, p, nj, b, s); }

@@ -180,12 +180,14 @@ class Net(torch.nn.Module):
 
     @torch.no_grad()
     def forward_offline(self, j2dc, accc, oric, first_tran=None, first_frame=False, lengths=None, use_graph=None,
-                        first_tran_mask=None, out=None):
+                        first_tran_mask=None, out=None, gravity=None):
         r"""``reset_states()`` then ``forward_online`` over every frame (evaluate.py:75-85, 93), natively batched.
 
         j2dc [T,33,3] or [B,T,33,3]; accc [..,T,6,3]; oric [..,T,6,3,3].  ``first_tran`` ([3] or [B,3]) and
         ``first_frame`` (bool or bool[B]) apply to frame 0; ``lengths`` (int[B]) marks ragged batches (outputs beyond
-        a sequence's length are zero).  Returns pose [..,T,24,3,3], tran [..,T,3] on the device of ``j2dc``.
+        a sequence's length are zero); ``gravity`` ([B,3], device inputs only) gives every sequence its own camera-frame gravity
+        (the reference sets ``net.gravityc`` per sequence, evaluate.py:73) instead of the class attribute.
+        Returns pose [..,T,24,3,3], tran [..,T,3] on the device of ``j2dc``.
         CPU inputs go through the end-to-end host entry point (H2D copy, kernels, D2H copy)."""
         lib = _lib.load()
         self._ensure_native()
@@ -220,6 +222,7 @@ class Net(torch.nn.Module):
             pose = torch.zeros(B, T, 24, 3, 3, **where)
             tran = torch.zeros(B, T, 3, **where)
         if on_cpu:
+            assert gravity is None, 'per-sequence gravity needs device inputs'
             _lib.check(lib.rc_forward_sequence_host(st, T, _lib.hptr(j), _lib.hptr(a), _lib.hptr(o),
                                                     _lib.hptr(ln), _lib.hptr(ft),
                                                     _lib.hptr(flags) if use_flags else None, _lib.hptr(pose), _lib.hptr(tran),
@@ -227,10 +230,11 @@ class Net(torch.nn.Module):
         else:
             dflags = flags.to(dev) if use_flags else None
             dln = None if ln is None else ln.to(dev)
-            _lib.check(lib.rc_forward_sequence(st, T, _lib.dptr(j), _lib.dptr(a), _lib.dptr(o), _lib.dptr(dln), None,
+            dgr = None if gravity is None else gravity.detach().reshape(B, 3).to(dev, torch.float32).contiguous()
+            _lib.check(lib.rc_forward_sequence(st, T, _lib.dptr(j), _lib.dptr(a), _lib.dptr(o), _lib.dptr(dln), _lib.dptr(dgr),
                                                _lib.dptr(ft), _lib.dptr(dflags), any_ff, _lib.dptr(pose), _lib.dptr(tran),
                                                int(use_graph), _lib.stream()))
-            self._keepalive = (j, a, o, ft, dflags, dln)   # kernels are still in flight
+            self._keepalive = (j, a, o, ft, dflags, dln, dgr)   # kernels are still in flight
         if single:
             return pose[0], tran[0]
         return pose, tran

@@ -278,6 +278,68 @@ def gen_metrics(ref, out):
     print('metrics', r3)
 
 
+def gen_pipeline(ref, out):
+    """SURVEY 8(f) rows 2 / 3.  (a) IMU synthesis exactly as preprocess.py:290-302 runs it (reference `_syn_acc`,
+    `body_model.forward_kinematics`, `vi_mask`, `ji_mask`); (b) the dataset-row -> network-input transforms of
+    evaluate.py:38-52 and 68-73, transcribed line by line on top of the reference's `articulate.math` (the statements live
+    inside `evaluate_aist_ours`, which needs the AIST++ files)."""
+    art = ref['art']
+    import preprocess as pp
+    g = torch.Generator().manual_seed(23)
+    d = {}
+    T = 40
+    aa = (torch.randn(1, 24, 3, generator=g) * 0.3 + torch.cumsum(torch.randn(T, 24, 3, generator=g) * 0.03, dim=0))
+    tran = torch.cumsum(torch.randn(T, 3, generator=g) * 0.02, dim=0)
+    shape = torch.randn(10, generator=g)
+    p = art.math.axis_angle_to_rotation_matrix(aa).view(-1, 24, 3, 3)
+    d['imu_pose'], d['imu_tran'], d['imu_shape'] = p, tran, shape
+    for tag, sh in (('mean', None), ('shaped', shape)):
+        grot, joint, vert = pp.body_model.forward_kinematics(p, sh, tran, calc_mesh=True)
+        d['imu_%s_vimu' % tag] = vert[:, pp.vi_mask]
+        d['imu_%s_acc' % tag] = pp._syn_acc(vert[:, pp.vi_mask])                  # preprocess.py:300
+        d['imu_%s_acc4' % tag] = pp._syn_acc(vert[:, pp.vi_mask], smooth_n=4)
+        d['imu_%s_ori' % tag] = grot[:, pp.ji_mask]                               # preprocess.py:301
+        d['imu_%s_joint' % tag] = joint
+    d['imu_short_acc'] = pp._syn_acc(d['imu_mean_vimu'][:5])                      # shorter than 2 * smooth_n + 1
+    # (b) two sequences, three rows (sequence 0 seen by two cameras, sequence 1 by one), ragged lengths
+    lens = [17, 9]
+    ori_w = [synthetic._random_rotations(L * 6, g).view(L, 6, 3, 3) for L in lens]
+    acc_w = [torch.randn(L, 6, 3, generator=g) * 3 for L in lens]
+    tran_w = [torch.randn(L, 3, generator=g) for L in lens]
+    pose_w = [torch.randn(L, 24, 3, generator=g) * 0.4 for L in lens]
+    rows = [(0, 0), (0, 1), (1, 0)]
+    cam_T, cam_K, j2d = [], [], []
+    for (i, j) in rows:
+        Tcw = torch.eye(4)
+        Tcw[:3, :3] = synthetic._random_rotations(1, g)[0]
+        Tcw[:3, 3] = torch.randn(3, generator=g) * 2
+        K = torch.tensor([[1000. + 50 * j, 0., 960. + 7 * i], [0., 990. + 30 * j, 540. - 5 * j], [0., 0., 1.]])
+        kp = torch.rand(lens[i], 33, 3, generator=g)
+        cam_T.append(Tcw); cam_K.append(K); j2d.append(kp)
+    for r, (i, j) in enumerate(rows):
+        Tcw, K = cam_T[r], cam_K[r]
+        oric = Tcw[:3, :3].matmul(ori_w[i])                                                                   # evaluate.py:43
+        accc = Tcw.matmul(art.math.append_zero(acc_w[i]).unsqueeze(-1)).squeeze(-1)[..., :3]                  # :44
+        j2dc = torch.zeros(len(oric), 33, 3)                                                                  # :45-49
+        j2dc[..., :2] = j2d[r][..., :2]
+        j2dc[..., 0] = j2dc[..., 0] * 1920
+        j2dc[..., 1] = j2dc[..., 1] * 1080
+        j2dc[..., -1] = j2d[r][..., -1]
+        pose = art.math.axis_angle_to_rotation_matrix(pose_w[i]).view(-1, 24, 3, 3)                           # :50-52
+        pose[:, 0] = Tcw[:3, :3].matmul(pose[:, 0])
+        tran = Tcw.matmul(art.math.append_one(tran_w[i]).unsqueeze(-1)).squeeze(-1)[..., :3]
+        j2dn = K.inverse().matmul(art.math.append_one(j2dc[..., :2]).unsqueeze(-1)).squeeze(-1)               # :70-72
+        j2dn[..., -1] = j2dc[..., -1]
+        grav = Tcw[:3, :3].mm(torch.tensor([0, -1, 0.]).view(3, 1)).view(3)                                   # :73
+        d['row%d_oric' % r], d['row%d_accc' % r], d['row%d_j2dc' % r] = oric, accc, j2dn
+        d['row%d_pose' % r], d['row%d_tran' % r], d['row%d_gravity' % r] = pose, tran, grav
+        d['row%d_cam_T' % r], d['row%d_cam_K' % r], d['row%d_j2d' % r] = Tcw, K, j2d[r]
+    for i in range(2):
+        d['seq%d_ori' % i], d['seq%d_acc' % i], d['seq%d_tran' % i], d['seq%d_pose_aa' % i] = ori_w[i], acc_w[i], tran_w[i], pose_w[i]
+    d['rows'] = torch.tensor(rows)
+    np.savez_compressed(os.path.join(out, 'pipeline.npz'), **{k: v.numpy() for k, v in d.items()})
+
+
 def art_noise(n, g, scale):
     aa = torch.randn(n, 3, generator=g) * scale
     ang = aa.norm(dim=1, keepdim=True)
@@ -291,7 +353,7 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref = import_reference()
-    which = sys.argv[1:] or ['math', 'kinematics', 'online', 'smplify', 'metrics']
+    which = sys.argv[1:] or ['math', 'kinematics', 'online', 'smplify', 'metrics', 'pipeline']
     with torch.no_grad():
         if 'math' in which:
             gen_math(ref, HERE)
@@ -299,6 +361,8 @@ def main():
             gen_kinematics(ref, HERE)
         if 'online' in which:
             gen_online(ref, HERE)
+        if 'pipeline' in which:
+            gen_pipeline(ref, HERE)
     if 'smplify' in which:
         gen_smplify(ref, HERE)
     if 'metrics' in which:
