@@ -215,6 +215,13 @@ int rc_synthesize_imu(const rc_model* m, const float* d_pose, const float* d_tra
                       const float* d_imu_vrest, const int32_t* h_vi, const int32_t* h_ji, int32_t n_imu, int32_t smooth_n, int64_t n,
                       float* d_acc, float* d_ori, float* d_joint, float* d_vimu, void* stream);
 
+/* Live wire formats (host code): the UDP datagram of live_detector.py:57-61 "uv(99)#ori(54)#acc(18)#RCM(9)" (comma-separated
+ * decimals, parsed like live_server.py:42-45: float() per token, then float32; h_rcm may be NULL) and the Unity TCP message of
+ * live_server.py:55-59 "%g,...(72 axis-angle values)#%g,%g,%g$".  rc_live_format_pose returns the number of bytes written
+ * (>= 0) or a negative rc_status. */
+int rc_live_parse_frame(const char* h_text, int32_t len, float* h_uv, float* h_ori, float* h_acc, float* h_rcm);
+int rc_live_format_pose(const float* h_pose_aa, const float* h_tran, char* h_out, int32_t cap);
+
 /* CUDA-event timing of the dominant kernel (the fused LSTM layers of rnn4: [rows, 2H] x [2H, 4H], H = 1280) for
  * bench.py's roofline: enable, run (non-graph launches), collect.  collect synchronises the device, returns the
  * summed duration of the recorded launches, their number, and the algorithmic FLOPs one stream-row costs in one

@@ -200,3 +200,66 @@ int rc_synthesize_imu(const rc_model* m, const float* d_pose, const float* d_tra
 }
 
 }  // extern "C"
+
+// ---- live wire formats (host code, no CUDA) ---------------------------------------------------------------------
+// live_detector.py:57-61 sends one UDP datagram per frame: four '#'-separated groups of comma-separated decimal numbers
+// "uv(99)#ori(54)#acc(18)#RCM(9)"; live_server.py:42-45 parses it with float() per token; live_server.py:55-59 answers Unity with
+// "%g,...(72 axis-angle)#%g,%g,%g$".
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+// parses up to `want` comma-separated numbers from [p, end); returns the count, -1 on a malformed token
+int parse_group(const char* p, const char* end, float* out, int want) {
+    int n = 0;
+    while (p < end) {
+        char* q = nullptr;
+        const double v = strtod(p, &q);          // float(token) then .float(): double parse, one rounding to float32
+        if (q == p) return -1;
+        if (n < want) out[n] = (float)v;
+        ++n;
+        p = q;
+        while (p < end && (*p == ' ' || *p == '\t')) ++p;
+        if (p < end) {
+            if (*p != ',') return -1;
+            ++p;
+        }
+    }
+    return n;
+}
+}  // namespace
+
+extern "C" {
+
+int rc_live_parse_frame(const char* h_text, int32_t len, float* h_uv, float* h_ori, float* h_acc, float* h_rcm) {
+    RC_ARG(h_text && len > 0 && h_uv && h_ori && h_acc);
+    std::string buf(h_text, h_text + len);       // strtod needs a terminated buffer
+    const char* p = buf.c_str();
+    const char* end = p + buf.size();
+    float* dst[4] = {h_uv, h_ori, h_acc, h_rcm};
+    const int want[4] = {99, 54, 18, 9};
+    float scratch[9];
+    for (int gidx = 0; gidx < 4; ++gidx) {
+        const char* sep = (const char*)memchr(p, '#', (size_t)(end - p));
+        const char* ge = sep ? sep : end;
+        if ((gidx < 3) != (sep != nullptr)) { rc_set_error("rc_live_parse_frame: expected 4 '#'-separated groups"); return RC_ERR_ARG; }
+        const int n = parse_group(p, ge, dst[gidx] ? dst[gidx] : scratch, want[gidx]);
+        if (n != want[gidx]) { rc_set_error("rc_live_parse_frame: group %d has %d numbers, expected %d", gidx, n, want[gidx]); return RC_ERR_ARG; }
+        p = ge + 1;
+    }
+    return RC_OK;
+}
+
+int rc_live_format_pose(const float* h_pose_aa, const float* h_tran, char* h_out, int32_t cap) {
+    RC_ARG(h_pose_aa && h_tran && h_out && cap > 0);
+    int pos = 0;
+    for (int i = 0; i < 75; ++i) {
+        const float v = i < 72 ? h_pose_aa[i] : h_tran[i - 72];
+        const int w = snprintf(h_out + pos, (size_t)(cap - pos), "%g%s", (double)v, i == 71 ? "#" : (i == 74 ? "$" : ","));
+        if (w < 0 || pos + w >= cap) { rc_set_error("rc_live_format_pose: buffer of %d bytes too small", cap); return RC_ERR_ARG; }
+        pos += w;
+    }
+    return pos;                                   // bytes written (no terminator counted)
+}
+
+}  // extern "C"

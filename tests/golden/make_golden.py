@@ -340,6 +340,35 @@ def gen_pipeline(ref, out):
     np.savez_compressed(os.path.join(out, 'pipeline.npz'), **{k: v.numpy() for k, v in d.items()})
 
 
+def gen_live(ref, out):
+    """the UDP text frame exactly as live_detector.py:57-61 builds it and the Unity message exactly as
+    live_server.py:55-59 builds it (statements transcribed; they sit inside socket loops)."""
+    import json
+    art = ref['art']
+    g = torch.Generator().manual_seed(5)
+    frames = []
+    for _ in range(3):
+        uv = torch.cat((torch.randn(33, 2, generator=g) * 0.2, torch.rand(33, 1, generator=g)), dim=1)
+        ori = synthetic._random_rotations(6, g)
+        acc = torch.randn(6, 3, generator=g) * 4
+        RCM = synthetic._random_rotations(1, g)[0]
+        uvn, orin, accn, RCMn = uv.numpy(), ori.numpy(), acc.numpy(), RCM.numpy()
+        data = (','.join([str(i) for i in uvn.reshape(-1)]) + '#' + ','.join(
+            [str(i) for i in orin.reshape(-1)]) + '#' + ','.join([str(i) for i in accn.reshape(-1)]) + '#' + ','.join(
+            [str(i) for i in RCMn.reshape(-1)])).encode()                                       # live_detector.py:57-60
+        # live_server.py:42-45
+        uv_s, ori_s, acc_s, rcm_s = data.decode().split('#')
+        conv = lambda x: np.asarray([float(i) for i in x.split(',')])
+        parsed = [torch.from_numpy(conv(x)).float() for x in (uv_s, ori_s, acc_s, rcm_s)]
+        pose = synthetic._random_rotations(24, g)
+        tran = torch.randn(3, generator=g) * torch.tensor([1e-3, 1.0, 1e4])
+        aa = art.math.rotation_matrix_to_axis_angle(pose).view(-1)                              # live_server.py:55
+        unity = ','.join(['%g' % v for v in aa]) + '#' + ','.join(['%g' % v for v in tran]) + '$'   # :57-58
+        frames.append({'datagram': data.decode(), 'uv': parsed[0].tolist(), 'ori': parsed[1].tolist(), 'acc': parsed[2].tolist(),
+                       'rcm': parsed[3].tolist(), 'pose_aa': [float(v) for v in aa], 'tran': [float(v) for v in tran], 'unity': unity})
+    json.dump(frames, open(os.path.join(out, 'live.json'), 'w'))
+
+
 def art_noise(n, g, scale):
     aa = torch.randn(n, 3, generator=g) * scale
     ang = aa.norm(dim=1, keepdim=True)
@@ -353,7 +382,7 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref = import_reference()
-    which = sys.argv[1:] or ['math', 'kinematics', 'online', 'smplify', 'metrics', 'pipeline']
+    which = sys.argv[1:] or ['math', 'kinematics', 'online', 'smplify', 'metrics', 'pipeline', 'live']
     with torch.no_grad():
         if 'math' in which:
             gen_math(ref, HERE)
@@ -363,6 +392,8 @@ def main():
             gen_online(ref, HERE)
         if 'pipeline' in which:
             gen_pipeline(ref, HERE)
+        if 'live' in which:
+            gen_live(ref, HERE)
     if 'smplify' in which:
         gen_smplify(ref, HERE)
     if 'metrics' in which:
