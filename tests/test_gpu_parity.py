@@ -221,6 +221,30 @@ def test_tensor_core_gemm_matches_simt(rb, body):
     net.set_gemm_mode(2)
 
 
+@pytest.mark.parametrize('B', [130, 300])
+def test_grouped_kernel_odd_row_blocks(rb, body, B):
+    """Persistent grouped kernel on CTA pairs with an odd number of 128-row blocks (the peer CTA of the last pair has no rows, or a
+    partial block), ragged lengths and mixed start modes, against the fp32 SIMT back end on the same batch."""
+    net = get_net(rb, body, 0, 'contact')
+    T = 8
+    inp = synthetic.make_inputs(B, T, seed=57, conf='mixed')
+    rb.Net.gravityc = inp['gravity'].clone()
+    j, a, o = inp['j2dc'].cuda(), inp['accc'].cuda(), inp['oric'].cuda()
+    ff = torch.arange(B) % 7 == 0
+    lengths = (torch.arange(B) % T + 1).to(torch.int32)
+    kw = dict(first_tran=torch.tensor([0., 0., 4.]), first_frame=ff, first_tran_mask=~ff, lengths=lengths)
+    net.set_gemm_mode(0)
+    p0, t0 = net.forward_offline(j, a, o, **kw)
+    net.set_gemm_mode(2)
+    for use_graph in (False, True):
+        p2, t2 = net.forward_offline(j, a, o, use_graph=use_graph, **kw)
+        valid = (torch.arange(T)[None, :] < lengths[:, None])                       # frames beyond a length are zero in both
+        ang = pose_angle(p0.cpu()[valid], p2.cpu()[valid])
+        assert ang.quantile(0.999).item() < 5e-5 and ang.max().item() < 5e-4, (B, use_graph, ang.max().item())
+        assert (t0 - t2).abs().max().item() < 1e-4
+        assert p2.cpu()[~valid].abs().max().item() == 0 and torch.equal(p0.cpu()[~valid], p2.cpu()[~valid])
+
+
 def test_offline_vs_oracle_seeded(rb, body, assets):
     """Seeded synthetic batch vs the CPU oracle (float32 and float64) — 24 sequences x 24 frames, all branches."""
     from oracle.kinematics import BodyOracle
