@@ -415,7 +415,28 @@ int build_phase(rc_state* s, int ph, const ChainSpec* ch, int nch) {
     return rc;
 }
 
+// The grouped kernel needs the maximum shared-memory carve-out (193 KB per CTA).  A kernel with another carve-out before or after
+// it makes the SMs re-partition L1 / shared memory, which drains them; asking for the same carve-out in the small per-frame
+// kernels of this path avoids that switch twice per grouped launch.
+int prefer_max_carveout() {
+    static bool done = false;
+    if (done) return RC_OK;
+    const int pct = cudaSharedmemCarveoutMaxShared;
+    RC_CUDA(cudaFuncSetAttribute(rc_prep_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RC_CUDA(cudaFuncSetAttribute(rc_lists_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RC_CUDA(cudaFuncSetAttribute(rc_mid_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RC_CUDA(cudaFuncSetAttribute(rc_kin_warp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RC_CUDA(cudaFuncSetAttribute(rc_init_scatter_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RC_CUDA(cudaFuncSetAttribute(rc_advance_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RC_CUDA(cudaFuncSetAttribute(rc_gemm_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    RC_CUDA(cudaFuncSetAttribute(rc_gemm_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    done = true;
+    return RC_OK;
+}
+
 int build_phases(rc_state* s) {
+    static const bool keep_carveout = getenv("RC_NO_CARVEOUT_HINT") != nullptr;      // A/B switch
+    if (!keep_carveout) RC_TRY(prefer_max_carveout());
     const rc_net* net = s->net;
     const long long Bpad = (long long)((s->B + 127) / 128) * 128;
     for (int i = 0; i < NNETS; ++i) {

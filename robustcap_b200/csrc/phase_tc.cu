@@ -397,7 +397,7 @@ __device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPhThreads, 1)
-rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT, long long* __restrict__ trace) {
+rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT, long long* __restrict__ trace, int korder) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bar_full[kPairStages];
@@ -479,22 +479,29 @@ rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, i
                 const int mb = 2 * tl.y + (int)rank;                            // this CTA's 128-row block
                 const RcPhJob& J = D->job[j];
                 if (trace && leader) { trace[(size_t)t * 16 + 0] = ((long long)blockIdx.x << 32) | (unsigned)((j << 16) | (tl.y << 8) | n); trace[(size_t)t * 16 + 1] = clock64(); }
-                if (J.dep >= 0) {
-                    const int need = D->job[J.dep].nt;
-                    const int* flag = ctl + 1 + J.dep * MT + mb;
-                    if (ld_relaxed_gpu(flag) < need) {                 // relaxed polls: every acquire load invalidates the SM's L1
-                        const long long t0 = clock64();
-                        while (ld_relaxed_gpu(flag) < need) {
-                            __nanosleep(32);
-                            if (clock64() - t0 > 4000000000LL) __trap();
-                        }
-                    }
-                    (void)ld_acquire_gpu(flag);
-                    fence_proxy_async_all();
-                }
-                if (trace && leader) trace[(size_t)t * 16 + 2] = clock64();
+                // K order of an LSTM layer: the h_prev half of [x | h_prev] first — the split pre-pass wrote it before the launch —, then
+                // the half the previous layer of this launch produces.  The dependency wait sits between the two, so the producing
+                // layer's epilogue / publish latency hides behind half of this tile's main loop (ramp of a phase, vision updater).
                 const int KB = J.K / kTcBK;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int KD = (J.kind == 1 && korder) ? KB / 2 : KB;  // K blocks that depend on the producing job
+                for (int i = 0; i < KB; ++i, ++it) {
+                    if (i == KB - KD) {
+                        if (J.dep >= 0) {
+                            const int need = D->job[J.dep].nt;
+                            const int* flag = ctl + 1 + J.dep * MT + mb;
+                            if (ld_relaxed_gpu(flag) < need) {         // relaxed polls: every acquire load invalidates the SM's L1
+                                const long long t0 = clock64();
+                                while (ld_relaxed_gpu(flag) < need) {
+                                    __nanosleep(32);
+                                    if (clock64() - t0 > 4000000000LL) __trap();
+                                }
+                            }
+                            (void)ld_acquire_gpu(flag);
+                            fence_proxy_async_all();
+                        }
+                        if (trace && leader) trace[(size_t)t * 16 + 2] = clock64();
+                    }
+                    const int kb = (i < KB - KD) ? KD + i : i - (KB - KD);
                     const int s = it % kPairStages;
                     const uint32_t ph = (it / kPairStages) & 1u;
                     if (kPairPrefetch > 0 && kb + kPairPrefetch < KB) {        // weights come from HBM on first touch: pull the tile's later K blocks into L2 early
@@ -743,7 +750,9 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
             attr_set = true;
         }
         const int pairs = std::max(1, std::min(sm_count() / 2, max_tiles));             // max_tiles bounds the 256-row tiles too
-        RC_LAUNCH(rc_tc_phase_pair_kernel, 2 * pairs, kPhThreads, kPairSmem, stream, d_desc, d_ctl, MT, d_trace);
+        static int korder = -1;
+        if (korder < 0) { const char* e = getenv("RC_PH_KORDER"); korder = e ? atoi(e) : 1; }   // 0: dependency wait before the first K block (A/B switch)
+        RC_LAUNCH(rc_tc_phase_pair_kernel, 2 * pairs, kPhThreads, kPairSmem, stream, d_desc, d_ctl, MT, d_trace, korder);
         RC_CHECK_LAUNCH();
         return RC_OK;
     }
@@ -768,6 +777,12 @@ int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int n
         work = std::max(work, (long long)B * (segs[i].Kout / 4));
     }
     a.nseg = nseg; a.zero = zero; a.nzero = nzero; a.advance = advance;
+    static bool attr_set = false;
+    if (!attr_set) {      // same shared-memory carve-out as the grouped kernel that follows (no L1 / shared re-partition between them)
+        if (!getenv("RC_NO_CARVEOUT_HINT"))
+            RC_CUDA(cudaFuncSetAttribute(rc_split_multi_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_set = true;
+    }
     dim3 grid((unsigned)std::max(1, (int)std::min<long long>(rc_cdiv(work, 256), 296)), (unsigned)nseg);
     RC_LAUNCH(rc_split_multi_kernel, grid, 256, 0, stream, a);
     RC_CHECK_LAUNCH();
