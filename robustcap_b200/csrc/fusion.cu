@@ -51,10 +51,12 @@ __global__ void __launch_bounds__(128) rc_prep_kernel(RcNetCfg cfg, const RcRowS
 }
 
 // one warp per list: ordered compaction of the flag predicates
-__global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __restrict__ lists, int* __restrict__ counts) {
+__global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __restrict__ lists, int* __restrict__ counts, int zero_init) {
+    rc_pdl_wait();
+    rc_pdl_trigger();
     const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (l >= NLISTS) return;
-    if (l == L_INIT) { if (lane == 0) counts[L_INIT] = 0; return; }
+    if (l == L_INIT) { if (lane == 0 && zero_init) counts[L_INIT] = 0; return; }
     int n = 0;
     constexpr int U = 8;                                       // flag loads in flight per lane (the loop is latency bound)
     for (int b0 = 0; b0 < B; b0 += 32 * U) {
@@ -82,6 +84,8 @@ __global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __res
 
 __global__ void __launch_bounds__(128) rc_mid_kernel(const int* __restrict__ flags, int B, const float* __restrict__ rcr,
                                                       const float* __restrict__ lerpw, const float* X3, const float* X6, float* X7) {
+    rc_pdl_wait();
+    rc_pdl_trigger();
     const int e = blockIdx.x * blockDim.x + threadIdx.x;           // one thread per (stream, joint)
     const int b = e / 23, i = e % 23;
     if (b >= B) return;
@@ -132,6 +136,8 @@ constexpr int kRowWarps = 4;
 __global__ void __launch_bounds__(kRowWarps * 32) rc_prep_warp_kernel(RcNetCfg cfg, const RcRowState* __restrict__ rows, StepIO io, int B,
                                                                        float* X2, float* X3, float* X4, float* X6, float* X7,
                                                                        float* rcr, float* conf, float* lerpw, int* flags, int* lists, int* counts) {
+    rc_pdl_wait();
+    rc_pdl_trigger();
     __shared__ RcPrepWarpSmem S[kRowWarps];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * kRowWarps + w;
@@ -164,6 +170,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) rc_kin_warp_kernel(RcNetCfg cf
                                                                       const float* __restrict__ rcr, const float* __restrict__ conf,
                                                                       const float* __restrict__ gravity_all, float* X4, float* X6,
                                                                       const float* X7, float* XI, int* lists, int* counts) {
+    rc_pdl_wait();
+    rc_pdl_trigger();
     __shared__ RcKinWarpSmem S[kRowWarps];
     __shared__ RcModelConst Ms;
     {   // SMPL constants once per block
@@ -462,8 +470,45 @@ int build_phases(rc_state* s) {
     return RC_OK;
 }
 
-int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr) {
-    RC_TRY(rc_tc_split_multi(s->ph_segs[ph], s->ph_nseg[ph], s->B, s->d_ctl[ph], 1 + RC_PH_MAXJOBS * s->ph_MT, stream, advance));
+// Debug timeline (RC_FRAME_TIMELINE=1, stream launches only): an event after every launch of the grouped path; rc_forward_sequence
+// prints the mean interval per slot over the frames of the call.
+struct FrameTimeline {
+    bool on = getenv("RC_FRAME_TIMELINE") != nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char*> tag;
+    size_t used = 0;
+    void mark(const char* t, void* stream) {
+        if (!on) return;
+        if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); tag.push_back(t); }
+        tag[used] = t;
+        cudaEventRecord(ev[used++], (cudaStream_t)stream);
+    }
+    void report(int slots_per_frame) {
+        if (!on || used < 2) { used = 0; return; }
+        cudaDeviceSynchronize();
+        std::map<std::string, std::pair<double, int>> acc;
+        std::vector<std::string> order;
+        for (size_t i = 1; i < used; ++i) {
+            if ((int)i < 2 * slots_per_frame) continue;                 // skip the first two frames
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            auto& a = acc[tag[i]];
+            if (a.second == 0) order.push_back(tag[i]);
+            a.first += ms; a.second += 1;
+        }
+        double tot = 0;
+        for (auto& k : order) tot += acc[k].first / acc[k].second;
+        fprintf(stderr, "[frame timeline, us per frame]");
+        for (auto& k : order) fprintf(stderr, " %s %.1f |", k.c_str(), 1e3 * acc[k].first / acc[k].second);
+        fprintf(stderr, " total %.1f\n", 1e3 * tot);
+        used = 0;
+    }
+};
+FrameTimeline g_tl;
+
+int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr, int* clear = nullptr) {
+    RC_TRY(rc_tc_split_multi(s->ph_segs[ph], s->ph_nseg[ph], s->B, s->d_ctl[ph], 1 + RC_PH_MAXJOBS * s->ph_MT, stream, advance, clear));
+    g_tl.mark(ph == PH_1 ? "split1" : ph == PH_2 ? "split2" : ph == PH_LATE ? "splitL" : "split6a", stream);
     if (s->prof_on) {                  // CUDA events right around the grouped GEMM launch, on the stream it is launched on
         if (s->prof_used + 2 > s->prof_ev.size()) {
             for (int q = 0; q < 256; ++q) { cudaEvent_t e; RC_CUDA(cudaEventCreate(&e)); s->prof_ev.push_back(e); }
@@ -472,10 +517,12 @@ int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr) {
     }
     RC_TRY(rc_tc_phase(s->d_phase[ph], s->d_ctl[ph], s->ph_MT, s->ph_max_tiles[ph], stream, s->d_trace[ph]));
     if (s->prof_on) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
+    g_tl.mark(ph == PH_1 ? "phase1" : ph == PH_2 ? "phase2" : ph == PH_LATE ? "phaseL" : "phase6a", stream);
     return RC_OK;
 }
 
-int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advance, void* stream) {
+// prep + list compaction, shared by every path
+int enqueue_prep(rc_state* s, const StepIO& io, void* stream, bool keep_init_list) {
     const rc_net* n = s->net;
     const int B = s->B;
     static const bool scalar_rows = getenv("RC_SCALAR_ROWS") != nullptr;     // validation switch: one-thread-per-stream kernels
@@ -483,37 +530,66 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
         RC_LAUNCH(rc_prep_kernel, rc_cdiv(B, 128), 128, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4, s->X6, s->X7,
                   s->rcr, s->conf, s->lerpw, s->flags);
     else
-        RC_LAUNCH(rc_prep_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4,
+        RC_LAUNCH_PDL(rc_prep_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, s->rows, io, B, s->X2, s->X3, s->X4,
                   s->X6, s->X7, s->rcr, s->conf, s->lerpw, s->flags, s->lists, s->counts);
     RC_CHECK_LAUNCH();
     if (B > 1 || scalar_rows) {
-        RC_LAUNCH(rc_lists_kernel, 1, NLISTS * 32, 0, stream, s->flags, B, s->lists, s->counts);
+        RC_LAUNCH_PDL(rc_lists_kernel, 1, NLISTS * 32, 0, stream, (const int*)s->flags, B, s->lists, s->counts, keep_init_list ? 0 : 1);
         RC_CHECK_LAUNCH();
     }
-    if (n->gemm_mode == 2 && s->ph_ready && B > 8) {
-        // persistent grouped kernel: rnn4 + rnn2 | mid | [rnn6 on first-frame rows] | rnn6 + rnn3 + rnn7 + rnn8 | kin | vision updater
-        // (rnn7 / rnn8 only need the outputs of rnn2 / rnn4 (:169-170), so they share a launch with rnn3 / rnn6)
-        RC_TRY(run_phase(s, PH_1, stream));
-        RC_LAUNCH(rc_mid_kernel, rc_cdiv((long long)B * 23, 128), 128, 0, stream, s->flags, B, s->rcr, s->lerpw, s->X3, s->X6, s->X7);
-        RC_CHECK_LAUNCH();
-        if (any_first_frame) RC_TRY(run_phase(s, PH_6A, stream));
-        RC_TRY(run_phase(s, PH_2, stream));
-        if (scalar_rows)
-            RC_LAUNCH(rc_kin_kernel, rc_cdiv(B, 64), 64, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B, io, s->Y7, s->Y8,
-                      s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
-        else
-            RC_LAUNCH(rc_kin_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B,
-                      io, s->Y7, s->Y8, s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
-        RC_CHECK_LAUNCH();
-        // init_net (re-seeds rnn2, :178-183) touches none of the vision updater's state: side stream.  The frame cursor is advanced by
-        // the updater's pre-pass (prep and kin, its only readers, are done).
-        static const bool serial2 = getenv("RC_SERIAL") != nullptr;
-        if (!serial2) { RC_CUDA(cudaEventRecord(s->ev_fork, (cudaStream_t)stream)); RC_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0)); }
-        RC_TRY(init_pass(s, serial2 ? stream : (void*)s->side));
-        RC_TRY(run_phase(s, PH_LATE, stream, advance ? s->d_t : nullptr));
-        if (!serial2) { RC_CUDA(cudaEventRecord(s->ev_join, s->side)); RC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_join, 0)); }
-        return RC_OK;
+    return RC_OK;
+}
+
+// Grouped path (gemm mode 2), first part of a frame: prep -> lists -> [rnn4 + rnn2] -> mid -> [rnn6 on first-frame rows] ->
+// [rnn6 + rnn3 + rnn7 + rnn8] -> kin (rnn7 / rnn8 only need the outputs of rnn2 / rnn4 (:169-170), so they share a launch with rnn3 / rnn6).
+int grouped_head(rc_state* s, const StepIO& io, int any_first_frame, void* stream) {
+    const rc_net* n = s->net;
+    const int B = s->B;
+    static const bool scalar_rows = getenv("RC_SCALAR_ROWS") != nullptr;
+    RC_TRY(enqueue_prep(s, io, stream, false));
+    g_tl.mark("prep+lists", stream);
+    RC_TRY(run_phase(s, PH_1, stream));
+    RC_LAUNCH_PDL(rc_mid_kernel, rc_cdiv((long long)B * 23, 128), 128, 0, stream, (const int*)s->flags, B, (const float*)s->rcr, (const float*)s->lerpw, (const float*)s->X3, (const float*)s->X6, s->X7);
+    RC_CHECK_LAUNCH();
+    g_tl.mark("mid", stream);
+    if (any_first_frame) RC_TRY(run_phase(s, PH_6A, stream));
+    RC_TRY(run_phase(s, PH_2, stream));
+    if (scalar_rows)
+        RC_LAUNCH(rc_kin_kernel, rc_cdiv(B, 64), 64, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B, io, s->Y7, s->Y8,
+                  s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
+    else
+        RC_LAUNCH_PDL(rc_kin_warp_kernel, rc_cdiv(B, kRowWarps), kRowWarps * 32, 0, stream, n->cfg, n->model->d_const, s->rows, s->flags, B,
+                  io, s->Y7, s->Y8, s->Y3, s->Y6, s->rcr, s->conf, s->gravity, s->X4, s->X6, s->X7, s->XI, s->lists, s->counts);
+    RC_CHECK_LAUNCH();
+    g_tl.mark("kin", stream);
+    return RC_OK;
+}
+
+// Second part: init_net (re-seeds rnn2, :178-183) on the side stream — its blocks (128 registers x 256 threads) cannot share an SM
+// with the resident grouped kernel, so it effectively runs after the vision updater — and the updater itself, whose pre-pass also
+// advances the frame cursor.
+int grouped_tail(rc_state* s, bool advance, void* stream) {
+    static const bool serial2 = getenv("RC_SERIAL") != nullptr;
+    if (!serial2) { RC_CUDA(cudaEventRecord(s->ev_fork, (cudaStream_t)stream)); RC_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0)); }
+    RC_TRY(init_pass(s, serial2 ? stream : (void*)s->side));
+    if (!serial2) RC_CUDA(cudaEventRecord(s->ev_join, s->side));
+    RC_TRY(run_phase(s, PH_LATE, stream, advance ? s->d_t : nullptr));
+    if (!serial2) RC_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_join, 0));
+    g_tl.mark("join", stream);
+    return RC_OK;
+}
+
+bool grouped_path(const rc_state* s) { return s->net->gemm_mode == 2 && s->ph_ready && s->B > 8; }
+
+int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advance, void* stream) {
+    const rc_net* n = s->net;
+    const int B = s->B;
+    static const bool scalar_rows = getenv("RC_SCALAR_ROWS") != nullptr;     // validation switch: one-thread-per-stream kernels
+    if (grouped_path(s)) {
+        RC_TRY(grouped_head(s, io, any_first_frame, stream));
+        return grouped_tail(s, advance, stream);
     }
+    RC_TRY(enqueue_prep(s, io, stream, false));
     // fork/join helpers: the side stream runs the chain that is independent of the main one (both inside the same graph when captured)
     static const bool serial = getenv("RC_SERIAL") != nullptr;               // validation switch: single stream
     cudaStream_t ms = (cudaStream_t)stream;
@@ -799,6 +875,7 @@ int rc_state_reset(rc_state* s, void* stream) {
     RC_CUDA(cudaMemsetAsync(s->X6, 0, (size_t)s->B * RC_K6 * sizeof(float), st));
     RC_CUDA(cudaMemsetAsync(s->X4, 0, (size_t)s->B * RC_K4 * sizeof(float), st));
     RC_CUDA(cudaMemsetAsync(s->d_t, 0, sizeof(int), st));
+    RC_CUDA(cudaMemsetAsync(s->counts, 0, NLISTS * sizeof(int), st));
     RC_LAUNCH(rc_reset_rows_kernel, rc_cdiv(s->B, 128), 128, 0, stream, s->rows, s->B, s->fresh ? 1 : 0);
     s->fresh = false;
     RC_CHECK_LAUNCH();
@@ -902,10 +979,13 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
     io.gravity = gravity; io.first_tran = first_tran; io.row_flags = row_flags; io.lengths = lengths;
     io.pose = pose; io.tran = tran; io.sp = (long long)T * 216; io.st = (long long)T * 3;
     io.d_t = s->d_t; io.first_mode = 2;
+    // (Tried: rotating the loop so that init_net of frame t overlaps prep + lists of frame t + 1 — its four launches take ~37 us on the
+    // side stream even when the list is empty, longer than prep + lists, so nothing was gained: 525 vs 527 us per frame.)
     RC_TRY(enqueue_step(s, io, any_first_frame, true, stream));
     if (T == 1) return RC_OK;
     if (!use_graph) {
         for (int t = 1; t < T; ++t) RC_TRY(enqueue_step(s, io, 0, true, stream));
+        g_tl.report(11);
         return RC_OK;
     }
     std::vector<const void*> key = {j2dc, accc, oric, lengths, gravity, first_tran, row_flags, pose, tran,
@@ -1045,15 +1125,15 @@ int rc_state_debug_phase_trace(rc_state* s, int enable, int phase, long long* ou
     if (enable) {
         for (int ph = 0; ph < PH_COUNT; ++ph) {
             if (s->d_trace[ph]) continue;
-            RC_TRY(dev_alloc(s->allocs, &s->d_trace[ph], (size_t)s->ph_max_tiles[ph] * 16));
-            RC_CUDA(cudaMemset(s->d_trace[ph], 0, (size_t)s->ph_max_tiles[ph] * 128));
+            RC_TRY(dev_alloc(s->allocs, &s->d_trace[ph], (size_t)(s->ph_max_tiles[ph] + 1) * 16));
+            RC_CUDA(cudaMemset(s->d_trace[ph], 0, (size_t)(s->ph_max_tiles[ph] + 1) * 128));
         }
         if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
     }
     if (out) {
         RC_ARG(phase >= 0 && phase < PH_COUNT && s->d_trace[phase]);
         RC_CUDA(cudaDeviceSynchronize());
-        const int n = std::min(max_tiles, s->ph_max_tiles[phase]);
+        const int n = std::min(max_tiles, s->ph_max_tiles[phase] + 1);
         RC_CUDA(cudaMemcpy(out, s->d_trace[phase], (size_t)n * 128, cudaMemcpyDeviceToHost));
         if (ntiles) *ntiles = s->ph_max_tiles[phase];
     }

@@ -410,8 +410,12 @@ rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, i
     __shared__ int tile_start[RC_PH_MAXJOBS + 1];
     __shared__ uint32_t tmem_base_s;
 
+    rc_pdl_wait();                                                              // the pre-pass (operands, zeroed control block) has completed
+    rc_pdl_trigger();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
+    unsigned long long t_entry = 0;
+    if (trace && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
     const bool leader = rank == 0;
     const int njobs = D->njobs;
 
@@ -437,6 +441,7 @@ rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, i
     }
     __syncthreads();
     const int total = tile_start[njobs];
+    long long* const tg = trace ? trace + (size_t)total * 16 : nullptr;        // (debug) row after the last tile: {~min entry, ~min first grab, max last publish, max exit} in globaltimer ns
     if ((int)(blockIdx.x >> 1) >= total) return;                               // uniform over the pair
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
@@ -478,7 +483,10 @@ rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, i
                 if (j < 0) break;
                 const int mb = 2 * tl.y + (int)rank;                            // this CTA's 128-row block
                 const RcPhJob& J = D->job[j];
-                if (trace && leader) { trace[(size_t)t * 16 + 0] = ((long long)blockIdx.x << 32) | (unsigned)((j << 16) | (tl.y << 8) | n); trace[(size_t)t * 16 + 1] = clock64(); }
+                if (trace && leader) {
+                    trace[(size_t)t * 16 + 0] = ((long long)blockIdx.x << 32) | (unsigned)((j << 16) | (tl.y << 8) | n); trace[(size_t)t * 16 + 1] = clock64();
+                    if (q == 0) { unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMax((unsigned long long*)tg + 1, ~g); }
+                }
                 // K order of an LSTM layer: the h_prev half of [x | h_prev] first — the split pre-pass wrote it before the launch —, then
                 // the half the previous layer of this launch produces.  The dependency wait sits between the two, so the producing
                 // layer's epilogue / publish latency hides behind half of this tile's main loop (ramp of a phase, vision updater).
@@ -679,9 +687,15 @@ rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, i
                 fence_proxy_async_all();
                 __threadfence();
                 red_release_gpu_add(ctl + 1 + t.x * MT + mb, 1);               // always, also for a row block beyond the list: consumers count tiles
-                if (tr_on) trace[(size_t)t.w * 16 + 7] = clock64();
+                if (tr_on) { trace[(size_t)t.w * 16 + 7] = clock64(); unsigned long long g; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g)); atomicMax((unsigned long long*)tg + 2, g); }
             }
         }
+    }
+    if (tg && threadIdx.x == 0) {
+        unsigned long long t_exit;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+        atomicMax((unsigned long long*)tg + 0, ~t_entry);                  // min via max of the complement (the row starts zeroed)
+        atomicMax((unsigned long long*)tg + 3, t_exit);
     }
     tc_fence_before();
     cluster_sync_all();                                                         // the leader's MMAs read the peer's shared memory until the end
@@ -696,12 +710,16 @@ struct SplitMultiArgs {
     int nzero;
     int* zero;
     int* advance;          // optional frame cursor to increment (sequence mode), nullptr otherwise
+    int* clear;            // optional int to reset to 0
 };
 
 __global__ void __launch_bounds__(256) rc_split_multi_kernel(const __grid_constant__ SplitMultiArgs a) {
+    rc_pdl_wait();
+    rc_pdl_trigger();
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         for (int i = threadIdx.x; i < a.nzero; i += blockDim.x) a.zero[i] = 0;
         if (a.advance && threadIdx.x == 0) *a.advance += 1;
+        if (a.clear && threadIdx.x == 0) *a.clear = 0;
     }
     const RcSplitSegM& g = a.seg[blockIdx.y];
     const int cnt = *g.count;
@@ -752,7 +770,7 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
         const int pairs = std::max(1, std::min(sm_count() / 2, max_tiles));             // max_tiles bounds the 256-row tiles too
         static int korder = -1;
         if (korder < 0) { const char* e = getenv("RC_PH_KORDER"); korder = e ? atoi(e) : 1; }   // 0: dependency wait before the first K block (A/B switch)
-        RC_LAUNCH(rc_tc_phase_pair_kernel, 2 * pairs, kPhThreads, kPairSmem, stream, d_desc, d_ctl, MT, d_trace, korder);
+        RC_LAUNCH_PDL(rc_tc_phase_pair_kernel, 2 * pairs, kPhThreads, kPairSmem, stream, d_desc, d_ctl, MT, d_trace, korder);
         RC_CHECK_LAUNCH();
         return RC_OK;
     }
@@ -767,7 +785,7 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
     return RC_OK;
 }
 
-int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance) {
+int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance, int* clear) {
     if (nseg < 1 || nseg > RC_PH_MAXSEGS) { rc_set_error("rc_tc_split_multi: %d segments", nseg); return RC_ERR_ARG; }
     SplitMultiArgs a;
     memset(&a, 0, sizeof(a));
@@ -776,7 +794,7 @@ int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int n
         a.seg[i] = segs[i];
         work = std::max(work, (long long)B * (segs[i].Kout / 4));
     }
-    a.nseg = nseg; a.zero = zero; a.nzero = nzero; a.advance = advance;
+    a.nseg = nseg; a.zero = zero; a.nzero = nzero; a.advance = advance; a.clear = clear;
     static bool attr_set = false;
     if (!attr_set) {      // same shared-memory carve-out as the grouped kernel that follows (no L1 / shared re-partition between them)
         if (!getenv("RC_NO_CARVEOUT_HINT"))
@@ -784,7 +802,7 @@ int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int n
         attr_set = true;
     }
     dim3 grid((unsigned)std::max(1, (int)std::min<long long>(rc_cdiv(work, 256), 296)), (unsigned)nseg);
-    RC_LAUNCH(rc_split_multi_kernel, grid, 256, 0, stream, a);
+    RC_LAUNCH_PDL(rc_split_multi_kernel, grid, 256, 0, stream, a);
     RC_CHECK_LAUNCH();
     return RC_OK;
 }

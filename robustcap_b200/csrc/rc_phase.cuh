@@ -42,4 +42,5 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
 // ([*, ld], first K columns valid, zero up to Kout) into (hi, lo)[compact row * pitch + col0 ...]; also zeroes `zero[0..nzero)`.
 struct RcSplitSegM { const float* src; int ld, K, Kout, col0, pitch; void* hi; void* lo; const int* rows; const int* count; };
 // `advance` (optional): an int the launch increments once (the sequence-mode frame cursor).
-int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance = nullptr);
+// `clear` (optional): an int the launch resets to 0.
+int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance = nullptr, int* clear = nullptr);

@@ -1,11 +1,16 @@
 // Rotation-representation conversion kernels (articulate/math/angular.py) + library-wide error plumbing.
 // HBM-bound streaming kernels: each block stages 128 items through shared memory so that global loads and
 // stores are fully coalesced although one thread converts one item.
+#include <stdlib.h>
 #include <stdarg.h>
 #include "rc_common.cuh"
 #include "rc_math.h"
 
 std::atomic<long long> g_rc_launches{0};
+bool rc_pdl_enabled() {
+    static const bool on = getenv("RC_NO_PDL") == nullptr;
+    return on;
+}
 static thread_local char g_err[512] = "";
 
 void rc_set_error(const char* fmt, ...) {

@@ -33,8 +33,9 @@ for ph in (0, 2, 3):
     buf = np.zeros((20000, 16), dtype=np.int64)
     nt = ctypes.c_int(0)
     _lib.check(lib.rc_state_debug_phase_trace(st, 0, ph, buf.ctypes.data_as(ctypes.c_void_p), buf.shape[0], ctypes.byref(nt)))
-    tr = buf[:nt.value]
-    tr = tr[tr[:, 1] != 0]
+    tr = buf[:nt.value + 1]
+    glob = tr[tr[:, 0] < 0]                       # kernel-wide stamps (complemented minima are negative as int64)
+    tr = tr[(tr[:, 1] != 0) & (tr[:, 0] >= 0)]
     cta = tr[:, 0] >> 32
     job = (tr[:, 0] >> 16) & 0xffff
     print('==== phase %d (%s): %d tiles on %d CTAs' % (ph, names[ph], len(tr), len(np.unique(cta))))
@@ -54,6 +55,11 @@ for ph in (0, 2, 3):
         s2 = job == jj
         print('   job %2d MMA thread waits (median cycles): tile descriptor %6d | accumulators handed back %6d | operand stages (sum over K blocks) %6d of %6d issue time' % (
             jj, np.median(tr[s2, 9]), np.median(tr[s2, 10]), np.median(tr[s2, 11]), np.median(mma[s2])))
+    if len(glob):
+        gl = glob[0]
+        t_entry, t_grab, t_pub, t_exit = ~int(gl[0]), ~int(gl[1]), int(gl[2]), int(gl[3])
+        print(' kernel-wide (globaltimer): first CTA entry -> first tile grab %.1f us | first grab -> last publish %.1f us | last publish -> last CTA exit %.1f us' % (
+            (t_grab - t_entry) * 1e-3, (t_pub - t_grab) * 1e-3, (t_exit - t_pub) * 1e-3))
     # per-CTA span and busy fraction
     spans, busy = [], []
     for c in np.unique(cta):
