@@ -410,9 +410,14 @@ int build_phase(rc_state* s, int ph, const ChainSpec* ch, int nch) {
             max_tiles += MT * j.nt;
         }
         const float* X = ni == NET2 ? s->X2 : ni == NET3 ? s->X3 : ni == NET4 ? s->X4 : ni == NET6 ? s->X6 : s->X7;
-        s->ph_segs[ph][nseg++] = RcSplitSegM{X, w.K1, w.K1, w.K1p, 0, w.K1p, Ph[0], Pl[0], rows, count};
-        s->ph_segs[ph][nseg++] = RcSplitSegM{nb.h[0], H, H, H, H, 2 * H, Ph[1], Pl[1], rows, count};
-        s->ph_segs[ph][nseg++] = RcSplitSegM{nb.h[1], H, H, H, H, 2 * H, Ph[2], Pl[2], rows, count};
+        RcSplitSegM sx{X, w.K1, w.K1, w.K1p, 0, w.K1p, Ph[0], Pl[0], rows, count, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (ni == NET7 || ni == NET8) {        // the joint blend ("mid", :154-167) is computed by the pre-pass; rnn7's segment also stores it for kin
+            sx.mid_flags = s->flags; sx.mid_rcr = s->rcr; sx.mid_lerpw = s->lerpw; sx.mid_x3 = s->X3; sx.mid_x6 = s->X6;
+            sx.mid_out = (ni == NET7) ? s->X7 : nullptr;
+        }
+        s->ph_segs[ph][nseg++] = sx;
+        s->ph_segs[ph][nseg++] = RcSplitSegM{nb.h[0], H, H, H, H, 2 * H, Ph[1], Pl[1], rows, count, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        s->ph_segs[ph][nseg++] = RcSplitSegM{nb.h[1], H, H, H, H, 2 * H, Ph[2], Pl[2], rows, count, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     }
     d->njobs = nj;
     if (rc == RC_OK) rc = dev_alloc(s->allocs, &s->d_phase[ph], (size_t)1);
@@ -549,9 +554,13 @@ int grouped_head(rc_state* s, const StepIO& io, int any_first_frame, void* strea
     RC_TRY(enqueue_prep(s, io, stream, false));
     g_tl.mark("prep+lists", stream);
     RC_TRY(run_phase(s, PH_1, stream));
-    RC_LAUNCH_PDL(rc_mid_kernel, rc_cdiv((long long)B * 23, 128), 128, 0, stream, (const int*)s->flags, B, (const float*)s->rcr, (const float*)s->lerpw, (const float*)s->X3, (const float*)s->X6, s->X7);
-    RC_CHECK_LAUNCH();
-    g_tl.mark("mid", stream);
+    // the joint blend ("mid") is fused into the second pre-pass (RcSplitSegM::mid_*); RC_MID_KERNEL=1 keeps the separate launch
+    static const bool mid_kernel = getenv("RC_MID_KERNEL") != nullptr;
+    if (mid_kernel) {
+        RC_LAUNCH_PDL(rc_mid_kernel, rc_cdiv((long long)B * 23, 128), 128, 0, stream, (const int*)s->flags, B, (const float*)s->rcr, (const float*)s->lerpw, (const float*)s->X3, (const float*)s->X6, s->X7);
+        RC_CHECK_LAUNCH();
+        g_tl.mark("mid", stream);
+    }
     if (any_first_frame) RC_TRY(run_phase(s, PH_6A, stream));
     RC_TRY(run_phase(s, PH_2, stream));
     if (scalar_rows)

@@ -29,6 +29,7 @@
 #include "rc_tc.cuh"
 #include "rc_tc_dev.cuh"
 #include "rc_phase.cuh"
+#include "rc_rows.h"
 
 namespace {
 
@@ -128,22 +129,27 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
                 if (j < 0) break;
                 const RcPhJob& J = D->job[j];
                 if (trace) { trace[(size_t)t * 16 + 0] = ((long long)blockIdx.x << 32) | (unsigned)((j << 16) | (m << 8) | n); trace[(size_t)t * 16 + 1] = clock64(); }
-                if (J.dep >= 0) {
-                    const int need = D->job[J.dep].nt;
-                    const int* flag = ctl + 1 + J.dep * MT + m;
-                    if (ld_relaxed_gpu(flag) < need) {                 // relaxed polls: every acquire load invalidates the SM's L1
-                        const long long t0 = clock64();
-                        while (ld_relaxed_gpu(flag) < need) {
-                            __nanosleep(32);
-                            if (clock64() - t0 > 4000000000LL) __trap();
-                        }
-                    }
-                    (void)ld_acquire_gpu(flag);
-                    fence_proxy_async_all();                    // the producer's generic-proxy stores before our async-proxy loads
-                }
-                if (trace) trace[(size_t)t * 16 + 2] = clock64();
+                // K order of an LSTM layer: the h_prev half first, the dependency wait in the middle (see the pair kernel)
                 const int KB = J.K / kTcBK;
-                for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int KD = (J.kind == 1) ? KB / 2 : KB;
+                for (int i = 0; i < KB; ++i, ++it) {
+                    if (i == KB - KD) {
+                        if (J.dep >= 0) {
+                            const int need = D->job[J.dep].nt;
+                            const int* flag = ctl + 1 + J.dep * MT + m;
+                            if (ld_relaxed_gpu(flag) < need) {
+                                const long long t0 = clock64();
+                                while (ld_relaxed_gpu(flag) < need) {
+                                    __nanosleep(32);
+                                    if (clock64() - t0 > 4000000000LL) __trap();
+                                }
+                            }
+                            (void)ld_acquire_gpu(flag);
+                            fence_proxy_async_all();
+                        }
+                        if (trace) trace[(size_t)t * 16 + 2] = clock64();
+                    }
+                    const int kb = (i < KB - KD) ? KD + i : i - (KB - KD);
                     const int s = it % kPhStages;
                     const uint32_t ph = (it / kPhStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
@@ -732,7 +738,24 @@ __global__ void __launch_bounds__(256) rc_split_multi_kernel(const __grid_consta
         const int r = g.rows[i];
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k < g.K) v = *reinterpret_cast<const float4*>(g.src + (size_t)r * g.ld + k);
-        const float x[4] = {v.x, v.y, v.z, v.w};
+        float x[4] = {v.x, v.y, v.z, v.w};
+        if (g.mid_flags && k + 3 >= 72 && k < 141) {              // joint blend of the rnn7 / rnn8 input, same arithmetic as rc_mid_joint
+            const int f = g.mid_flags[r];
+            float rcr[9], lw[2];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) rcr[q] = g.mid_rcr[r * 9 + q];
+            lw[0] = g.mid_lerpw[r * 2]; lw[1] = g.mid_lerpw[r * 2 + 1];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int col = k + j;
+                if (col < 72 || col >= 141) continue;
+                const int jt = (col - 72) / 3, c = (col - 72) % 3;
+                float out[3];
+                rc_mid_joint(f, rcr, lw, g.mid_x3 + (size_t)r * RC_K3 + 72 + jt * 3, g.mid_x6 + (size_t)r * RC_K6 + 171 + jt * 3, out);
+                x[j] = out[c];
+                if (g.mid_out) g.mid_out[(size_t)r * RC_K7 + col] = x[j];
+            }
+        }
         __half hi[4], lo[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -760,7 +783,10 @@ int sm_count() {
 
 int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void* stream, long long* d_trace) {
     static int pair = -1;
-    if (pair < 0) { const char* e = getenv("RC_PH_PAIR"); pair = e ? atoi(e) : 1; }       // RC_PH_PAIR=0: single-CTA kernel
+    // Default: the single-CTA kernel (128-row tiles).  RC_PH_PAIR=1 selects the CTA-pair kernel (cta_group::2, 256-row tiles): 25 % less
+    // L2 -> SM traffic, same main-loop rate (both sit at the shared-memory port), but the row lists of a frame (~768 / ~256 streams) end
+    // in a mostly empty 256-row tile more often, so it is ~2 % slower on the mixed-confidence workload (same-box A/B: 544 vs 535 us).
+    if (pair < 0) { const char* e = getenv("RC_PH_PAIR"); pair = e ? atoi(e) : 0; }
     if (pair) {
         static bool attr_set = false;
         if (!attr_set) {

@@ -40,7 +40,13 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
 
 // Gather + split pre-pass for all chains of a phase in one launch: segment i copies rows rows_i[0..*count_i) of src
 // ([*, ld], first K columns valid, zero up to Kout) into (hi, lo)[compact row * pitch + col0 ...]; also zeroes `zero[0..nzero)`.
-struct RcSplitSegM { const float* src; int ld, K, Kout, col0, pitch; void* hi; void* lo; const int* rows; const int* count; };
+struct RcSplitSegM {
+    const float* src; int ld, K, Kout, col0, pitch; void* hi; void* lo; const int* rows; const int* count;
+    // optional "mid" fusion (net/sig_mp.py:154-167): columns [72, 141) of the rnn7 / rnn8 input are the vision / inertial joint blend,
+    // computed here from the row's flags, Rcr, lerp weights and the rnn2 / rnn4 outputs instead of being read from src;
+    // mid_out (one of the two segments) also stores them to the fp32 input row for the kin kernel.
+    const int* mid_flags; const float* mid_rcr; const float* mid_lerpw; const float* mid_x3; const float* mid_x6; float* mid_out;
+};
 // `advance` (optional): an int the launch increments once (the sequence-mode frame cursor).
 // `clear` (optional): an int the launch resets to 0.
 int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance = nullptr, int* clear = nullptr);
