@@ -312,9 +312,11 @@ def main():
     if args.gemm_mode == 2:
         # dominant kernel = the persistent grouped GEMM; its launches of one frame run the whole LSTM stack of every stream once
         dom_flop = fpr.value * B * T * args.steps
-        kname = ('rc_tc_phase_pair_kernel (persistent grouped tcgen05 GEMM on CTA pairs, cta_group::2 M=256: all linear1 / LSTM / linear2 '
-                 'layers of a phase of the frame in one launch, 3 launches per frame; kind::f16 on split-fp16 operands, 3 MMAs per '
-                 'fp32-accurate product; CUDA events around every launch)')
+        pair = os.environ.get('RC_PH_PAIR', '0') not in ('', '0')
+        kname = (('rc_tc_phase_pair_kernel (persistent grouped tcgen05 GEMM on CTA pairs, cta_group::2 M=256' if pair else
+                  'rc_tc_phase_kernel (persistent grouped tcgen05 GEMM, one CTA per SM, 128 x 128 tiles from a global queue') +
+                 ': all linear1 / LSTM / linear2 layers of a phase of the frame in one launch, 3 launches per frame; kind::f16 on split-fp16 '
+                 'operands, 3 MMAs per fp32-accurate product; CUDA events around every launch)')
     else:
         # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
         dom_flop = fpr.value * 2 * B * T * args.steps

@@ -51,7 +51,8 @@ for ph in (0, 2, 3):
         s = job == jj
         f = lambda x: '%7d/%-8d' % (np.median(x[s]), x[s].max())
         print(' %3d %6d | %s %s %s %s %s %s %s' % (jj, s.sum(), f(dep), f(fill), f(mma), f(lag), f(epa), f(epb), f(tot)))
-    for jj in np.unique(job):
+    pair_kernel = os.environ.get('RC_PH_PAIR', '0') not in ('', '0')        # slots 9-11 hold the MMA-thread waits only in the pair kernel
+    for jj in (np.unique(job) if pair_kernel else []):
         s2 = job == jj
         print('   job %2d MMA thread waits (median cycles): tile descriptor %6d | accumulators handed back %6d | operand stages (sum over K blocks) %6d of %6d issue time' % (
             jj, np.median(tr[s2, 9]), np.median(tr[s2, 10]), np.median(tr[s2, 11]), np.median(mma[s2])))
