@@ -51,12 +51,12 @@ __global__ void __launch_bounds__(128) rc_prep_kernel(RcNetCfg cfg, const RcRowS
 }
 
 // one warp per list: ordered compaction of the flag predicates
-__global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __restrict__ lists, int* __restrict__ counts, int zero_init) {
+__global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __restrict__ lists, int* __restrict__ counts) {
     rc_pdl_wait();
     rc_pdl_trigger();
     const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (l >= NLISTS) return;
-    if (l == L_INIT) { if (lane == 0 && zero_init) counts[L_INIT] = 0; return; }
+    if (l == L_INIT) { if (lane == 0) counts[L_INIT] = 0; return; }
     int n = 0;
     constexpr int U = 8;                                       // flag loads in flight per lane (the loop is latency bound)
     for (int b0 = 0; b0 < B; b0 += 32 * U) {
@@ -511,8 +511,8 @@ struct FrameTimeline {
 };
 FrameTimeline g_tl;
 
-int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr, int* clear = nullptr) {
-    RC_TRY(rc_tc_split_multi(s->ph_segs[ph], s->ph_nseg[ph], s->B, s->d_ctl[ph], 1 + RC_PH_MAXJOBS * s->ph_MT, stream, advance, clear));
+int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr) {
+    RC_TRY(rc_tc_split_multi(s->ph_segs[ph], s->ph_nseg[ph], s->B, s->d_ctl[ph], 1 + RC_PH_MAXJOBS * s->ph_MT, stream, advance));
     g_tl.mark(ph == PH_1 ? "split1" : ph == PH_2 ? "split2" : ph == PH_LATE ? "splitL" : "split6a", stream);
     if (s->prof_on) {                  // CUDA events right around the grouped GEMM launch, on the stream it is launched on
         if (s->prof_used + 2 > s->prof_ev.size()) {
@@ -527,7 +527,7 @@ int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr, int* cl
 }
 
 // prep + list compaction, shared by every path
-int enqueue_prep(rc_state* s, const StepIO& io, void* stream, bool keep_init_list) {
+int enqueue_prep(rc_state* s, const StepIO& io, void* stream) {
     const rc_net* n = s->net;
     const int B = s->B;
     static const bool scalar_rows = getenv("RC_SCALAR_ROWS") != nullptr;     // validation switch: one-thread-per-stream kernels
@@ -539,7 +539,7 @@ int enqueue_prep(rc_state* s, const StepIO& io, void* stream, bool keep_init_lis
                   s->X6, s->X7, s->rcr, s->conf, s->lerpw, s->flags, s->lists, s->counts);
     RC_CHECK_LAUNCH();
     if (B > 1 || scalar_rows) {
-        RC_LAUNCH_PDL(rc_lists_kernel, 1, NLISTS * 32, 0, stream, (const int*)s->flags, B, s->lists, s->counts, keep_init_list ? 0 : 1);
+        RC_LAUNCH_PDL(rc_lists_kernel, 1, NLISTS * 32, 0, stream, (const int*)s->flags, B, s->lists, s->counts);
         RC_CHECK_LAUNCH();
     }
     return RC_OK;
@@ -551,7 +551,7 @@ int grouped_head(rc_state* s, const StepIO& io, int any_first_frame, void* strea
     const rc_net* n = s->net;
     const int B = s->B;
     static const bool scalar_rows = getenv("RC_SCALAR_ROWS") != nullptr;
-    RC_TRY(enqueue_prep(s, io, stream, false));
+    RC_TRY(enqueue_prep(s, io, stream));
     g_tl.mark("prep+lists", stream);
     RC_TRY(run_phase(s, PH_1, stream));
     // the joint blend ("mid") is fused into the second pre-pass (RcSplitSegM::mid_*); RC_MID_KERNEL=1 keeps the separate launch
@@ -598,7 +598,7 @@ int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advanc
         RC_TRY(grouped_head(s, io, any_first_frame, stream));
         return grouped_tail(s, advance, stream);
     }
-    RC_TRY(enqueue_prep(s, io, stream, false));
+    RC_TRY(enqueue_prep(s, io, stream));
     // fork/join helpers: the side stream runs the chain that is independent of the main one (both inside the same graph when captured)
     static const bool serial = getenv("RC_SERIAL") != nullptr;               // validation switch: single stream
     cudaStream_t ms = (cudaStream_t)stream;

@@ -19,9 +19,11 @@
 // read and the gate math runs.  The epilogue is off the critical path as long as it is shorter than a tile's main loop.
 //
 // Cross-CTA hand-over of an activation row block: the epilogue's st.global (generic proxy) must be visible to the consumer's
-// TMA loads (async proxy): writer = stores, fence.proxy.async, __threadfence, CTA barrier, red.release.gpu; reader =
-// ld.acquire.gpu spin, fence.proxy.async, TMA.  The queue is handed out in dependency order (a tile only depends on tiles with a
-// smaller index, which are finished or held by a running CTA), so the scheme cannot deadlock whatever the residency.
+// TMA loads (async proxy): writer = stores, CTA barrier of the epilogue warps, then ONE thread's fence.proxy.async +
+// __threadfence + red.release.gpu (cumulative over what the barrier ordered); reader = relaxed polls + one ld.acquire.gpu,
+// fence.proxy.async, TMA.  An LSTM tile loads the h_prev half of its K range first (written before the launch) and only then
+// waits for the producing layer.  The queue is handed out in dependency order (a tile only depends on tiles with a smaller
+// index, which are finished or held by a running CTA), so the scheme cannot deadlock whatever the residency.
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -716,7 +718,6 @@ struct SplitMultiArgs {
     int nzero;
     int* zero;
     int* advance;          // optional frame cursor to increment (sequence mode), nullptr otherwise
-    int* clear;            // optional int to reset to 0
 };
 
 __global__ void __launch_bounds__(256) rc_split_multi_kernel(const __grid_constant__ SplitMultiArgs a) {
@@ -725,7 +726,6 @@ __global__ void __launch_bounds__(256) rc_split_multi_kernel(const __grid_consta
     if (blockIdx.x == 0 && blockIdx.y == 0) {
         for (int i = threadIdx.x; i < a.nzero; i += blockDim.x) a.zero[i] = 0;
         if (a.advance && threadIdx.x == 0) *a.advance += 1;
-        if (a.clear && threadIdx.x == 0) *a.clear = 0;
     }
     const RcSplitSegM& g = a.seg[blockIdx.y];
     const int cnt = *g.count;
@@ -811,7 +811,7 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
     return RC_OK;
 }
 
-int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance, int* clear) {
+int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance) {
     if (nseg < 1 || nseg > RC_PH_MAXSEGS) { rc_set_error("rc_tc_split_multi: %d segments", nseg); return RC_ERR_ARG; }
     SplitMultiArgs a;
     memset(&a, 0, sizeof(a));
@@ -820,7 +820,7 @@ int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int n
         a.seg[i] = segs[i];
         work = std::max(work, (long long)B * (segs[i].Kout / 4));
     }
-    a.nseg = nseg; a.zero = zero; a.nzero = nzero; a.advance = advance; a.clear = clear;
+    a.nseg = nseg; a.zero = zero; a.nzero = nzero; a.advance = advance;
     static bool attr_set = false;
     if (!attr_set) {      // same shared-memory carve-out as the grouped kernel that follows (no L1 / shared re-partition between them)
         if (!getenv("RC_NO_CARVEOUT_HINT"))

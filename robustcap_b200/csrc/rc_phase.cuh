@@ -48,5 +48,4 @@ struct RcSplitSegM {
     const int* mid_flags; const float* mid_rcr; const float* mid_lerpw; const float* mid_x3; const float* mid_x6; float* mid_out;
 };
 // `advance` (optional): an int the launch increments once (the sequence-mode frame cursor).
-// `clear` (optional): an int the launch resets to 0.
-int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance = nullptr, int* clear = nullptr);
+int rc_tc_split_multi(const RcSplitSegM* segs, int nseg, int B, int* zero, int nzero, void* stream, int* advance = nullptr);
