@@ -50,36 +50,51 @@ __global__ void __launch_bounds__(128) rc_prep_kernel(RcNetCfg cfg, const RcRowS
                            conf + b, lerpw + b * 2);
 }
 
-// one warp per list: ordered compaction of the flag predicates
-__global__ void rc_lists_kernel(const int* __restrict__ flags, int B, int* __restrict__ lists, int* __restrict__ counts) {
+// ordered compaction of the flag predicates into the five row lists: one 1024-thread block, a ballot per warp and list, a scan of
+// the 32 warp counts (the one-warp-per-list version took 7.8 us per frame, mostly serial rounds of dependent flag loads)
+__global__ void __launch_bounds__(1024) rc_lists_kernel(const int* __restrict__ flags, int B, int* __restrict__ lists, int* __restrict__ counts) {
     rc_pdl_wait();
     rc_pdl_trigger();
-    const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (l >= NLISTS) return;
-    if (l == L_INIT) { if (lane == 0) counts[L_INIT] = 0; return; }
-    int n = 0;
-    constexpr int U = 8;                                       // flag loads in flight per lane (the loop is latency bound)
-    for (int b0 = 0; b0 < B; b0 += 32 * U) {
-        int f[U];
+    constexpr int NL = L_INIT;                                   // the lists built here: L_ALL .. L_LATE
+    __shared__ int wcount[NL][32];
+    __shared__ int running[NL];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < NL) running[threadIdx.x] = 0;
+    if (threadIdx.x == 0) counts[L_INIT] = 0;
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + threadIdx.x;
+        const int f = (b < B) ? flags[b] : 0;
+        const bool act = (f & RC_F_ACTIVE) != 0;
+        bool p[NL];
+        p[L_ALL] = act;
+        p[L_HI] = act && (f & RC_F_HI);
+        p[L_6A] = act && (f & RC_F_FIRST_FRAME);
+        p[L_6B] = act && (f & RC_F_R6B);
+        p[L_LATE] = act && (f & RC_F_LATE);
+        unsigned m[NL];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int b = b0 + u * 32 + lane;
-            f[u] = (b < B) ? flags[b] : 0;
+        for (int l = 0; l < NL; ++l) {
+            m[l] = __ballot_sync(0xffffffffu, p[l]);
+            if (lane == 0) wcount[l][warp] = __popc(m[l]);
         }
+        __syncthreads();
+        if (warp < NL) {                                         // exclusive scan of the 32 warp counts of list `warp`
+            const int c = wcount[warp][lane];
+            int incl = c;
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int b = b0 + u * 32 + lane;
-            bool p = (f[u] & RC_F_ACTIVE) != 0;
-            if (l == L_HI) p = p && (f[u] & RC_F_HI);
-            else if (l == L_6A) p = p && (f[u] & RC_F_FIRST_FRAME);
-            else if (l == L_6B) p = p && (f[u] & RC_F_R6B);
-            else if (l == L_LATE) p = p && (f[u] & RC_F_LATE);
-            const unsigned m = __ballot_sync(0xffffffffu, p);
-            if (p) lists[l * B + n + __popc(m & ((1u << lane) - 1u))] = b;
-            n += __popc(m);
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            wcount[warp][lane] = running[warp] + incl - c;
+            __syncwarp();
+            if (lane == 31) running[warp] += incl;
         }
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < NL; ++l)
+            if (p[l]) lists[l * B + wcount[l][warp] + __popc(m[l] & ((1u << lane) - 1u))] = b;
+        __syncthreads();
     }
-    if (lane == 0) counts[l] = n;
+    if (threadIdx.x < NL) counts[threadIdx.x] = running[threadIdx.x];
 }
 
 __global__ void __launch_bounds__(128) rc_mid_kernel(const int* __restrict__ flags, int B, const float* __restrict__ rcr,
@@ -539,7 +554,7 @@ int enqueue_prep(rc_state* s, const StepIO& io, void* stream) {
                   s->X6, s->X7, s->rcr, s->conf, s->lerpw, s->flags, s->lists, s->counts);
     RC_CHECK_LAUNCH();
     if (B > 1 || scalar_rows) {
-        RC_LAUNCH_PDL(rc_lists_kernel, 1, NLISTS * 32, 0, stream, (const int*)s->flags, B, s->lists, s->counts);
+        RC_LAUNCH_PDL(rc_lists_kernel, 1, 1024, 0, stream, (const int*)s->flags, B, s->lists, s->counts);
         RC_CHECK_LAUNCH();
     }
     return RC_OK;
