@@ -243,8 +243,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        pose, tran = net.forward_offline(j, a, o, first_tran=ft, use_graph=False)
+    out_p = torch.empty(B, T, 24, 3, 3, device=dev)
+    out_t = torch.empty(B, T, 3, device=dev)
+
+    def step(graph=True):
+        # graph=True is the default behaviour of Net.forward_offline (frames 1..T-1 replay one captured CUDA graph)
+        pose, tran = net.forward_offline(j, a, o, first_tran=ft, use_graph=graph, out=(out_p, out_t))
         if dist is not None:
             dist.gather(pose, gather_pose, dst=0)
             dist.gather(tran, gather_tran, dst=0)
@@ -254,7 +258,6 @@ def main():
         step()
     barrier()
     st = net._states[B]
-    _lib.check(lib.rc_profile_enable(st, 1))
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = lib.rc_launch_count()
@@ -268,7 +271,19 @@ def main():
     ms_total = e0.elapsed_time(e1)
     launches = lib.rc_launch_count() - launches0
     clk = clocks.stop()
+    # Roofline pass: the same K steps once more with plain stream launches, so that CUDA events can sit right around every launch
+    # of the dominant kernel on its launch stream (kernels inside a graph replay cannot be bracketed).  Same kernels, same data.
     import ctypes
+    step(False)
+    barrier()
+    _lib.check(lib.rc_profile_enable(st, 1))
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(args.steps):
+        step(False)
+    r1.record()
+    barrier()
+    roof_ms_total = r0.elapsed_time(r1)
     tot_ms, nl, fpr = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
     _lib.check(lib.rc_profile_collect(st, ctypes.byref(tot_ms), ctypes.byref(nl), ctypes.byref(fpr)))
     _lib.check(lib.rc_profile_enable(st, 0))
@@ -287,12 +302,12 @@ def main():
     ht = torch.empty(B, T, 3).pin_memory()
     hft = torch.tensor([0., 0., 4.])
     for _ in range(2):
-        net.forward_offline(hj, ha, ho, first_tran=hft, use_graph=False, out=(hp, ht))
+        net.forward_offline(hj, ha, ho, first_tran=hft, out=(hp, ht))
     barrier()
     t0 = time.perf_counter()
     reps = max(2, min(args.steps, 3))
     for _ in range(reps):
-        net.forward_offline(hj, ha, ho, first_tran=hft, use_graph=False, out=(hp, ht))
+        net.forward_offline(hj, ha, ho, first_tran=hft, out=(hp, ht))
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / reps
     t_e = torch.tensor([e2e_ms], device=dev)
@@ -327,7 +342,8 @@ def main():
                 'bound': 'tensor',
                 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': dom_tflops / pk['tflops_sustained'], 'peak_source': 'bf16 sustained, of ' + pk['source'],
-                'traffic': dominant_traffic(args.gemm_mode), 'launches': int(nl.value), 'share_of_step': tot_ms.value / ms_total,
+                'traffic': dominant_traffic(args.gemm_mode), 'launches': int(nl.value), 'share_of_step': tot_ms.value / roof_ms_total,
+                'timed_with': 'a second pass of the same K steps with stream launches (%.1f ms per step) — the value pass replays a CUDA graph' % (roof_ms_total / args.steps),
                 'tensor_pipe_frac': 3 * dom_tflops / pk['tflops_sustained'],   # 3 fp16 MMAs are issued per algorithmic fp32 product
                 'whole_path_tflops': FLOP_PER_FRAME * B * T / (ms_step * 1e-3) / 1e12,
                 'weight_stream_gbs': WEIGHT_BYTES * T / (ms_step * 1e-3) / 1e9}
@@ -336,7 +352,8 @@ def main():
             'data': 'synthetic',
             'config': {'workload': 'offline_eval %d seq x %d frames per GPU (BASELINE configs[2])' % (B, T), 'conf': args.conf,
                        'weights': 'random-init seed 0 (contact variant)', 'l2': 'inputs (%.0f MB) + weights (243 MB) per step exceed the 126 MB L2'
-                       % ((hj.numel() + ha.numel() + ho.numel()) * 4 / 1e6), 'final_gather': 'nccl gather to rank 0 inside the timed region' if world > 1 else 'none'},
+                       % ((hj.numel() + ha.numel() + ho.numel()) * 4 / 1e6), 'final_gather': 'nccl gather to rank 0 inside the timed region' if world > 1 else 'none',
+                       'launch': 'CUDA-graph replay of the per-frame launch sequence (Net.forward_offline default)'},
             'clocks': clk, 'gpu_launches': int(launches),
             'e2e': {'value': frames_step / (e2e_ms / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'ms_per_step': e2e_ms},
