@@ -37,13 +37,15 @@ def pack_row(j2d, imu_acc, imu_ori, cam_T, cam_K, image_size=(1920, 1080), pose_
 
 
 def syn_acc(v, smooth_n=2):
-    """preprocess.py:22-33."""
-    mid = smooth_n // 2
-    acc = torch.stack([(v[i] + v[i + 2] - 2 * v[i + 1]) * 3600 for i in range(0, v.shape[0] - 2)])
-    acc = torch.cat((torch.zeros_like(acc[:1]), acc, torch.zeros_like(acc[:1])))
-    if mid != 0 and v.shape[0] > 2 * smooth_n:
-        acc[smooth_n:-smooth_n] = torch.stack([(v[i] + v[i + smooth_n * 2] - 2 * v[i + smooth_n]) * 3600 / smooth_n ** 2
-                                               for i in range(0, v.shape[0] - smooth_n * 2)])
+    """preprocess.py:22-33 restated with slices: central second differences at 60 fps (x 3600), zero at both ends; away from the ends
+    (``smooth_n <= t < T - smooth_n``) the stencil is widened to +-smooth_n frames and divided by smooth_n^2.  Element for element the
+    same float32 operations in the same order as the reference's list comprehensions."""
+    T = v.shape[0]
+    acc = torch.zeros_like(v)
+    acc[1:T - 1] = (v[:T - 2] + v[2:] - 2 * v[1:T - 1]) * 3600
+    s = smooth_n
+    if s // 2 != 0 and T > 2 * s:
+        acc[s:T - s] = (v[:T - 2 * s] + v[2 * s:] - 2 * v[s:T - s]) * 3600 / s ** 2
     return acc
 
 
