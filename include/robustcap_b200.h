@@ -221,6 +221,8 @@ int rc_synthesize_imu(const rc_model* m, const float* d_pose, const float* d_tra
  * (>= 0) or a negative rc_status. */
 int rc_live_parse_frame(const char* h_text, int32_t len, float* h_uv, float* h_ori, float* h_acc, float* h_rcm);
 int rc_live_format_pose(const float* h_pose_aa, const float* h_tran, char* h_out, int32_t cap);
+/* The sensor server's binary datagram (live_demo_sync.py:262-268, get_from_udp): float32[8 n] = t[n] | q[n,4] (wxyz) | a[n,3]. */
+int rc_live_parse_imu_packet(const void* h_data, int32_t nbytes, int32_t n_imu, float* h_t, float* h_q, float* h_a);
 
 /* CUDA-event timing of the dominant kernel (the fused LSTM layers of rnn4: [rows, 2H] x [2H, 4H], H = 1280) for
  * bench.py's roofline: enable, run (non-graph launches), collect.  collect synchronises the device, returns the

@@ -250,6 +250,17 @@ int rc_live_parse_frame(const char* h_text, int32_t len, float* h_uv, float* h_o
     return RC_OK;
 }
 
+// live_demo_sync.py:262-268 (get_from_udp): the sensor server's binary datagram is float32[8 N] = t[N] | q[N,4] (wxyz) | a[N,3]
+int rc_live_parse_imu_packet(const void* h_data, int32_t nbytes, int32_t n_imu, float* h_t, float* h_q, float* h_a) {
+    RC_ARG(h_data && n_imu > 0 && h_t && h_q && h_a);
+    if (nbytes != 32 * n_imu) { rc_set_error("rc_live_parse_imu_packet: %d bytes, expected %d for %d sensors", nbytes, 32 * n_imu, n_imu); return RC_ERR_ARG; }
+    const unsigned char* p = (const unsigned char*)h_data;          // the datagram need not be aligned
+    memcpy(h_t, p, (size_t)n_imu * 4);
+    memcpy(h_q, p + (size_t)n_imu * 4, (size_t)n_imu * 16);
+    memcpy(h_a, p + (size_t)n_imu * 20, (size_t)n_imu * 12);
+    return RC_OK;
+}
+
 int rc_live_format_pose(const float* h_pose_aa, const float* h_tran, char* h_out, int32_t cap) {
     RC_ARG(h_pose_aa && h_tran && h_out && cap > 0);
     int pos = 0;

@@ -12,7 +12,7 @@ import torch
 from . import _lib
 from . import math as M
 
-__all__ = ['parse_frame', 'format_pose', 'LiveSession']
+__all__ = ['parse_frame', 'format_pose', 'parse_imu_packet', 'LiveSession']
 
 
 def parse_frame(datagram: bytes):
@@ -33,6 +33,14 @@ def format_pose(pose_aa: torch.Tensor, tran: torch.Tensor) -> bytes:
     if n < 0:
         _lib.check(n)
     return buf.raw[:n]
+
+
+def parse_imu_packet(data: bytes, n_imu: int):
+    """``t`` (list of n floats), ``q [n,4]`` (wxyz), ``a [n,3]`` of the sensor server's binary datagram (live_demo_sync.py:262-268)."""
+    lib = _lib.load()
+    t, q, a = torch.empty(n_imu), torch.empty(n_imu, 4), torch.empty(n_imu, 3)
+    _lib.check(lib.rc_live_parse_imu_packet(data, len(data), int(n_imu), _lib.hptr(t), _lib.hptr(q), _lib.hptr(a)))
+    return t.tolist(), q, a
 
 
 class LiveSession:

@@ -40,6 +40,20 @@ def test_format_pose_matches_reference(live):
         assert msg.decode() == f['unity']
 
 
+def test_parse_imu_packet_matches_reference(live):
+    """live_demo_sync.py:262-268 (get_from_udp), statement for statement."""
+    import numpy as np
+    from robustcap_b200.live import parse_imu_packet
+    N = 6
+    raw = np.random.RandomState(3).randn(8 * N).astype(np.float32).tobytes()
+    data = np.frombuffer(raw, np.float32).copy()
+    t, q, a = data[:N], data[N:5 * N].reshape(N, 4), data[5 * N:].reshape(N, 3)
+    gt, gq, ga = parse_imu_packet(raw, N)
+    assert gt == t.tolist() and torch.equal(gq, torch.from_numpy(q)) and torch.equal(ga, torch.from_numpy(a))
+    with pytest.raises(RuntimeError):
+        parse_imu_packet(raw[:-4], N)
+
+
 @pytest.mark.gpu
 def test_live_session_vs_oracle(live, assets):
     if not torch.cuda.is_available():
