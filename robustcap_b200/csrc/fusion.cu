@@ -741,6 +741,7 @@ int rc_net_create(rc_net** out, const rc_model* model, const rc_net_config* cfg)
 int rc_net_set_config(rc_net* n, const rc_net_config* cfg) {
     RC_ARG(n && cfg);
     apply_cfg(n, cfg);
+    n->cfg_version += 1;        // cached CUDA graphs of every state of this net hold the old config by value: they re-capture
     return RC_OK;
 }
 
@@ -962,7 +963,7 @@ int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const f
     } else if (first_frame) {
         RC_TRY(enqueue_step(s, io, 1, false, stream));          // extra rnn6 pass (sig_mp.py:155-156): direct launches
     } else {
-        if (!s->on_graph || s->on_graph_stream != stream) {
+        if (!s->on_graph || s->on_graph_stream != stream || s->on_graph_cfg_version != s->net->cfg_version) {
             if (s->on_graph) { cudaGraphExecDestroy(s->on_graph); s->on_graph = nullptr; }
             cudaGraph_t g = nullptr;
             if (!s->cap_stream) RC_CUDA(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
@@ -978,6 +979,7 @@ int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const f
             cudaGraphDestroy(g);
             if (e != cudaSuccess) { s->on_graph = nullptr; rc_set_error("graph instantiate: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
             s->on_graph_stream = stream;
+            s->on_graph_cfg_version = s->net->cfg_version;
         }
         RC_CUDA(cudaGraphLaunch(s->on_graph, st));
         g_rc_launches.fetch_add(s->on_graph_nodes);
@@ -1013,7 +1015,8 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
         return RC_OK;
     }
     std::vector<const void*> key = {j2dc, accc, oric, lengths, gravity, first_tran, row_flags, pose, tran,
-                                    (const void*)(intptr_t)T, (const void*)stream, (const void*)(intptr_t)s->net->gemm_mode};
+                                    (const void*)(intptr_t)T, (const void*)stream, (const void*)(intptr_t)s->net->gemm_mode,
+                                    (const void*)(intptr_t)s->net->cfg_version};
     if (!s->graph || key != s->graph_key) {
         if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
         cudaGraph_t g = nullptr;
@@ -1066,6 +1069,10 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* hj, const floa
     if (hfl) {
         RC_CUDA(cudaMemcpyAsync(s->hfl, hfl, B * sizeof(int), cudaMemcpyHostToDevice, st));
         for (size_t b = 0; b < B; ++b) any_ff |= (hfl[b] & RC_ROW_FIRST_FRAME);
+    }
+    if (hlen) {        // frames beyond a sequence's length are never written: they must read back as zeros, not stale data
+        RC_CUDA(cudaMemsetAsync(s->hp, 0, B * T * 216 * sizeof(float), st));
+        RC_CUDA(cudaMemsetAsync(s->ht, 0, B * T * 3 * sizeof(float), st));
     }
     RC_TRY(rc_forward_sequence(s, T, s->hj, s->ha, s->ho, hlen ? s->hlen : nullptr, nullptr, hft ? s->hft : nullptr,
                                hfl ? s->hfl : nullptr, any_ff, s->hp, s->ht, use_graph, stream));

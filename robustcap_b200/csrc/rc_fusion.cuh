@@ -50,6 +50,7 @@ struct rc_net {
     int gemm_mode = 2;          // 0 = fp32 SIMT tiles, 1 = tcgen05 split-fp16, one launch per layer, 2 = tcgen05 persistent
                                 // grouped kernel, one launch per phase of the frame (batches > 8 streams)
     bool tc_ready = false;
+    int cfg_version = 0;        // bumped by rc_net_set_config: captured CUDA graphs bake the config into kernel arguments
 };
 
 struct rc_state {
@@ -104,6 +105,7 @@ struct rc_state {
     cudaGraphExec_t on_graph = nullptr;
     void* on_graph_stream = nullptr;
     long long on_graph_nodes = 0;
+    int on_graph_cfg_version = -1;
     // single-stream cooperative kernel (stream.cu)
     unsigned* sk_bar = nullptr;
     int* sk_rows = nullptr;            // [0] = row 0, [1] = count 1, [4..5] = frame flags / need_init

@@ -17,14 +17,13 @@ class RNNDataset(torch.utils.data.Dataset):
         else:
             self.data, self.label = data, label
         self.augment_fn = augment_fn
-        self.device = device
+        self.device = data[0].device if device is None else device       # rnn.py:60: default = where data[0] lives
 
     def __getitem__(self, i):
-        data = self.data[i] if self.augment_fn is None else self.augment_fn(self.data[i])
-        label = self.label[i]
-        if self.device is None:
-            return data, label
-        return data.to(self.device), label.to(self.device)
+        item = self.data[i]
+        if self.augment_fn is not None:
+            item = self.augment_fn(item)
+        return item.to(self.device), self.label[i].to(self.device)
 
     def __len__(self):
         return len(self.data)

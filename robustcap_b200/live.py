@@ -49,11 +49,14 @@ class LiveSession:
         self.RCM = None
         self.stran = None
 
-    def feed(self, datagram: bytes) -> bytes:
+    def feed(self, datagram: bytes):
+        """Returns the Unity message, or ``None`` for the very first datagram: ``run_live_demo`` only reads the calibration
+        ``RCM`` (and sets the instance's gravity) from it and starts inference with the next one (live_server.py:32-35)."""
         uv, ori, acc, rcm = parse_frame(datagram)
-        if self.RCM is None:                                                    # live_server.py:33-35
+        if self.RCM is None:                                                    # live_server.py:32-35
             self.RCM = rcm
-            type(self.net).gravityc = torch.matmul(rcm, torch.tensor([0., -1, 0.]).unsqueeze(-1)).squeeze(-1)
+            self.net.gravityc = torch.matmul(rcm, torch.tensor([0., -1, 0.]).unsqueeze(-1)).squeeze(-1)   # on the instance
+            return None
         pose, tran = self.net.forward_online(uv, acc, ori, first_frame=self.stran is None)   # :46-48
         pose = pose.clone()
         pose[0] = self.RCM.T.matmul(pose[0])                                    # :49-50

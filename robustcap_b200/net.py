@@ -65,6 +65,12 @@ class Net(torch.nn.Module):
         self._grav_pushed = {}
         self._dirty = True
         self._use_graph = True
+        self._fp = None
+        # Any load into a sub-module (net.rnn2.load_state_dict(...), RNN(load_weight_file=...) as the reference's training / merge
+        # scripts do, sig_mp.py:850-857) must reach the packed device copy too, not only Net.load_state_dict.
+        mark = lambda module, incompatible: setattr(self, '_dirty', True)
+        for m in self.modules():
+            m.register_load_state_dict_post_hook(mark)
 
     # ---- native plumbing -------------------------------------------------------------------------------------------
     def _config(self):
@@ -95,9 +101,19 @@ class Net(torch.nn.Module):
         except Exception:
             pass
 
-    def _ensure_native(self):
+    def _fingerprint(self):
+        # storage address + in-place version counter of every parameter: catches `p.data = ...`, `p.copy_()`, optimiser steps
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def mark_dirty(self):
+        """Force a re-upload of the weights on the next call (after editing parameters in a way torch cannot see)."""
+        self._dirty = True
+
+    def _ensure_native(self, check_params=False):
         lib = _lib.load()
         _lib.require_cuda()
+        if check_params and not self._dirty and self._fingerprint() != self._fp:
+            self._dirty = True
         if self._net is not None and not self._dirty:
             cfg = self._config()
             key = bytes(cfg)
@@ -116,6 +132,7 @@ class Net(torch.nn.Module):
             _lib.check(lib.rc_net_set_tensor(h, key.encode(), _lib.hptr(t), t.numel()))
         _lib.check(lib.rc_net_finalize(h))
         self._dirty = False
+        self._fp = self._fingerprint()
 
     def _state(self, B):
         lib = _lib.load()
@@ -148,8 +165,12 @@ class Net(torch.nn.Module):
 
     # ---- reference API -------------------------------------------------------------------------------------------
     def reset_states(self):
-        r"""Reset the hidden states and the tracker variables of the online stream. sig_mp.py:95-104."""
-        if self._net is not None and 1 in self._states:
+        r"""Reset the hidden states and the tracker variables of the online stream (the B = 1 state ``forward_online`` uses;
+        ``forward_offline`` resets its own batch state at the start of every call). sig_mp.py:95-104.
+        Also the point where in-place parameter edits since the last call are detected (per-frame calls only see loads)."""
+        if self._net is not None and not self._dirty and self._fingerprint() != self._fp:
+            self._dirty = True
+        if self._net is not None and not self._dirty and 1 in self._states:
             _lib.check(_lib.load().rc_state_reset(self._states[1], _lib.stream()))
 
     @staticmethod
@@ -190,7 +211,7 @@ class Net(torch.nn.Module):
         Returns pose [..,T,24,3,3], tran [..,T,3] on the device of ``j2dc``.
         CPU inputs go through the end-to-end host entry point (H2D copy, kernels, D2H copy)."""
         lib = _lib.load()
-        self._ensure_native()
+        self._ensure_native(check_params=True)
         dev = _lib.require_cuda()
         single = j2dc.dim() == 3
         if single:

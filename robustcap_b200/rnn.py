@@ -3,12 +3,10 @@ r"""``RNN`` / ``RNNWithInit`` parameter containers (reference ``articulate/utils
 ``Net.forward_online`` never calls ``RNN.forward``; it drives the sub-modules ``linear1 / rnn / linear2 / init_net``
 directly (net/sig_mp.py:126-129, 182).  Here the modules only carry the parameters under the reference's
 ``state_dict`` names, so checkpoints load unchanged; the arithmetic happens in the CUDA library after
-``Net`` packs these tensors (``rc_net_set_tensor``).  ``forward`` over lists of sequences (the training-time API)
-is kept for compatibility on top of torch's own LSTM and is not part of the hot path.
+``Net`` packs these tensors (``rc_net_set_tensor``).  ``forward`` over lists of padded sequences is the reference's
+TRAINING-time API (net/sig_mp.py:301-857, out of scope): it raises and points at the reference.
 """
 import torch
-from torch.nn.functional import relu
-from torch.nn.utils.rnn import pad_sequence, pack_padded_sequence, pad_packed_sequence
 
 __all__ = ['RNN', 'RNNWithInit']
 
@@ -29,12 +27,8 @@ class RNN(torch.nn.Module):
                 self.eval()
 
     def forward(self, x, init=None):
-        r"""List of [num_frames, input_size] -> list of [num_frames, output_size]. rnn.py:120-133."""
-        length = [_.shape[0] for _ in x]
-        x = self.dropout(relu(self.linear1(pad_sequence(x))))
-        x = self.rnn(pack_padded_sequence(x, length, enforce_sorted=False), init)[0]
-        x = self.linear2(pad_packed_sequence(x)[0])
-        return [x[:l, i].clone() for i, l in enumerate(length)]
+        raise RuntimeError('robustcap_b200.rnn.RNN only carries parameters for Net (inference hot path); the padded-sequence '
+                           'training forward is articulate/utils/torch/rnn.py:120-133 of the reference and is out of scope here')
 
 
 class RNNWithInit(RNN):
@@ -54,9 +48,3 @@ class RNNWithInit(RNN):
                 self.load_state_dict(torch.load(load_weight_file, map_location=torch.device('cpu')))
                 self.eval()
 
-    def forward(self, x, _=None):
-        r"""rnn.py:207-219."""
-        x, x_init = list(zip(*x))
-        nd, nh = self.rnn.num_layers, self.rnn.hidden_size
-        h, c = self.init_net(torch.stack(x_init)).view(-1, 2, nd, nh).permute(1, 2, 0, 3)
-        return super(RNNWithInit, self).forward(x, (h.contiguous(), c.contiguous()))

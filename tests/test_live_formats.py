@@ -71,9 +71,11 @@ def test_live_session_vs_oracle(live, assets):
     fmt = lambda x: ','.join(str(v) for v in x.numpy().reshape(-1))
     sess = LiveSession(net)
     msgs = []
+    mk = lambda t: '#'.join((fmt(inp['j2dc'][0, t]), fmt(inp['oric'][0, t]), fmt(inp['accc'][0, t]), fmt(RCM))).encode()
+    assert sess.feed(mk(0)) is None          # the first datagram only calibrates (live_server.py:32-35), like the reference
+    assert torch.equal(rb.Net.gravityc, torch.tensor([-0.0029, 0.9980, -0.0273]))     # gravity lands on the instance, not the class
     for t in range(10):
-        dg = '#'.join((fmt(inp['j2dc'][0, t]), fmt(inp['oric'][0, t]), fmt(inp['accc'][0, t]), fmt(RCM))).encode()
-        msgs.append(sess.feed(dg).decode())
+        msgs.append(sess.feed(mk(t)).decode())
     grav = RCM @ torch.tensor([0., -1, 0.])
     o = FusionOracle(sd, BodyOracle(assets['smpl_file']))
     op, ot = o.run(inp['j2dc'][0], inp['accc'][0], inp['oric'][0], first_frame=True, gravity=grav)
