@@ -235,6 +235,13 @@ int rc_profile_collect(rc_state* s, double* total_ms, int64_t* launches, double*
  * b * width floats (width = 69,3,69,3,144,2). */
 int rc_state_debug_output(rc_state* s, int which, float* h_out, void* stream);
 
+/* Debug / parity aid: `d_log` (device, int32 [B, T], caller-owned; NULL switches it off) receives, for every frame the following
+ * rc_forward_sequence calls process, which data-dependent decisions the translation / contact / floor logic took
+ * (net/sig_mp.py:185-225): bit 1 contact branch (:190), 2 contact argmax, 4 tran snapped to pc (:200-201), 8 tran lerped to pc
+ * (:203), 16 floor sample stored (:208-214), 32 / 64 floor snap through the far / near foot (:217-221), 128 rnn2 re-seeded by
+ * init_net (:178-183).  Parity tests report the first frame where the CUDA path and the oracle disagree and which bit flipped. */
+int rc_state_set_branch_log(rc_state* s, int32_t* d_log);
+
 /* Debug tap of the persistent grouped GEMM kernel (gemm mode 2): enable != 0 makes every later launch record, per tile, 16 int64
  * {cta<<32|job<<16|row block<<8|column tile, clock64 at: grab, dependency met, first MMA, last commit, accumulators seen by the
  * epilogue, outputs stored, tile published, then finer epilogue stamps}; with h_out != NULL the trace of `phase` (0 rnn4+rnn2, 1 rnn6 on

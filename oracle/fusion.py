@@ -127,8 +127,13 @@ class FusionOracle:
 
     # ---- one frame ---------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, j2dc, accc, oric, first_tran=None, first_frame=False, trace=None):
+    def step(self, j2dc, accc, oric, first_tran=None, first_frame=False, trace=None, branches=None):
+        """``branches`` (optional list): receives one int per frame describing the data-dependent decisions of the translation /
+        contact / floor logic, same bit layout as the CUDA path's debug log (``rc_rows.h`` RC_BR_*): 1 contact branch, 2 contact
+        argmax, 4 snap to pc, 8 lerp to pc, 16 floor sample stored, 32 floor snap (other foot), 64 floor snap (near foot),
+        128 rnn2 re-seeded by init_net."""
         dt = self.dtype
+        br = 0
         j2dc, accc, oric = j2dc.to(dt).reshape(33, 3), accc.to(dt).reshape(6, 3), oric.to(dt).reshape(6, 3, 3)
         lo, hi = self.conf_range
         N = self.nets
@@ -172,6 +177,7 @@ class FusionOracle:
 
         if c >= hi and self.first_reach:                                       # :178-183
             self.first_reach = False
+            br |= 128
             z = j3dr.reshape(-1)
             for n, (w, b) in enumerate(self.init_net):
                 z = torch.addmv(b, w, z)
@@ -187,14 +193,17 @@ class FusionOracle:
             v = (Rcr @ vr.view(3, 1)).view(3) * VEL_SCALE / 60
         else:
             v = (self.last_pfoot - pfoot)[int(contact.argmax())]
+            br |= 1 | (2 * int(contact.argmax()))
         tran = v if self.last_tran is None else self.last_tran + v             # :191-194
 
         if hi <= c:                                                            # :196-203
             k = min((c - lo) / (hi - lo), 1)
             if bool((pc - tran).norm() > self.distance_threshold) or self.tran_filter_num > 1:
                 tran = pc
+                br |= 4
             else:
                 tran = rot.lerp(tran, pc, self.tran_filter_num * k)
+                br |= 8
         tran = tran.reshape(3)
 
         g = self.gravity.to(dt)
@@ -204,14 +213,17 @@ class FusionOracle:
             p0 = torch.dot(pfoot[0] + tran, g) * g
             p1 = torch.dot(pfoot[1] + tran, g) * g
             self.floor_y.append(p1 if bool(p0.norm() < p1.norm()) else p0)
+            br |= 16
         if self.use_flat_floor and len(self.floor_y) > 10 and bool(cmax > thr):  # :215-221
             p0 = torch.dot(pfoot[0] + tran, g) * g
             p1 = torch.dot(pfoot[1] + tran, g) * g
             mean = sum(self.floor_y[-6:]) / 6
             if bool(p0.norm() < p1.norm()) and bool((mean - p1).norm() < hthr):
                 tran = tran + (mean - p1)
+                br |= 32
             elif bool((mean - p0).norm() < hthr):
                 tran = tran + (mean - p0)
+                br |= 64
         if first_tran is not None:                                             # :222-225
             tran = first_tran.to(dt).reshape(3)
         elif first_frame:
@@ -239,9 +251,11 @@ class FusionOracle:
             run(4, self._cat(accc, oric, self._normalise_keypoints(kp)))
 
         self.last_tran = tran                                                  # :273
+        if branches is not None:
+            branches.append(br)
         return pose.view(24, 3, 3).clone(), tran.view(3).clone()
 
-    def run(self, j2dc, accc, oric, first_tran=None, first_frame=False, gravity=None, reset=True, trace=None):
+    def run(self, j2dc, accc, oric, first_tran=None, first_frame=False, gravity=None, reset=True, trace=None, branches=None):
         """forward_offline := reset + per-frame forward_online (evaluate.py:75-85, 93)."""
         if reset:
             self.reset()
@@ -250,7 +264,7 @@ class FusionOracle:
         poses, trans = [], []
         for t in range(j2dc.shape[0]):
             kw = {'first_tran': first_tran, 'first_frame': first_frame} if t == 0 else {}
-            p, tr = self.step(j2dc[t], accc[t], oric[t], trace=trace, **kw)
+            p, tr = self.step(j2dc[t], accc[t], oric[t], trace=trace, branches=branches, **kw)
             poses.append(p)
             trans.append(tr)
         return torch.stack(poses), torch.stack(trans)

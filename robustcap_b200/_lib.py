@@ -111,6 +111,7 @@ _SIGS = {
     'rc_live_parse_frame': (i32, [ctypes.c_char_p, i32, vp, vp, vp, vp]),
     'rc_live_format_pose': (i32, [vp, vp, ctypes.c_char_p, i32]),
     'rc_live_parse_imu_packet': (i32, [ctypes.c_char_p, i32, i32, vp, vp, vp]),
+    'rc_state_set_branch_log': (i32, [vp, vp]),
     'rc_profile_enable': (i32, [vp, i32]),
     'rc_profile_collect': (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]),
 }

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(64) rc_kin_kernel(RcNetCfg cfg, const RcModelC
     if (f & RC_F_FIRST_TRAN) for (int i = 0; i < 3; ++i) ft[i] = io.first_tran[(size_t)b * 3 + i];
     RcRowState st = rows[b];
     const int need_init = rc_kin_row(cfg, *M, &st, f, y7, Y8 + b * 4, Y3 + b * 4, Y6 + b * 4, r, conf[b], g, ft, pose, tran,
-                                     X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6);
+                                     X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6, io.branch ? io.branch + b * io.sb + t : nullptr);
     rows[b] = st;
     float* po = io.pose + b * io.sp + (long long)t * 216;
     float* to = io.tran + b * io.st + (long long)t * 3;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) rc_kin_warp_kernel(RcNetCfg cf
     if (f & RC_F_FIRST_TRAN) for (int i = 0; i < 3; ++i) ft[i] = io.first_tran[(size_t)b * 3 + i];
     const int need_init = rc_kin_warp(cfg, Ms, S[w], rows + b, f, Y7 + (size_t)b * 144, y8, vr, pc, r, conf[b], g, ft,
                                       io.pose + b * io.sp + (long long)t * 216, io.tran + b * io.st + (long long)t * 3,
-                                      X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6, lane);
+                                      X4 + (size_t)b * RC_K4, X6 + (size_t)b * RC_K6, lane, io.branch ? io.branch + b * io.sb + t : nullptr);
     if (need_init) {
         for (int i = lane; i < kInitK0; i += 32) XI[(size_t)b * kInitK0 + i] = (i < 69) ? X7[(size_t)b * RC_K7 + 72 + i] : 0.f;
         if (lane == 0) lists[L_INIT * B + atomicAdd(&counts[L_INIT], 1)] = b;
@@ -1005,6 +1005,7 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
     io.gravity = gravity; io.first_tran = first_tran; io.row_flags = row_flags; io.lengths = lengths;
     io.pose = pose; io.tran = tran; io.sp = (long long)T * 216; io.st = (long long)T * 3;
     io.d_t = s->d_t; io.first_mode = 2;
+    io.branch = s->branch_log; io.sb = T;
     // (Tried: rotating the loop so that init_net of frame t overlaps prep + lists of frame t + 1 — its four launches take ~37 us on the
     // side stream even when the list is empty, longer than prep + lists, so nothing was gained: 525 vs 527 us per frame.)
     RC_TRY(enqueue_step(s, io, any_first_frame, true, stream));
@@ -1016,7 +1017,7 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
     }
     std::vector<const void*> key = {j2dc, accc, oric, lengths, gravity, first_tran, row_flags, pose, tran,
                                     (const void*)(intptr_t)T, (const void*)stream, (const void*)(intptr_t)s->net->gemm_mode,
-                                    (const void*)(intptr_t)s->net->cfg_version};
+                                    (const void*)(intptr_t)s->net->cfg_version, (const void*)s->branch_log};
     if (!s->graph || key != s->graph_key) {
         if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
         cudaGraph_t g = nullptr;
@@ -1107,6 +1108,14 @@ int rc_state_debug_lstm(rc_state* s, int ni, int layer, int mode, const float* x
         a.W = w.WL[layer]; a.bias = w.bL[layer]; a.N = 4 * w.H; a.Nw = 4 * w.H; a.C = c; a.Hout = hout; a.H = w.H;
         RC_TRY(launch_linear(a, B, true, stream));
     }
+    return RC_OK;
+}
+
+// Debug / parity aid: `log` (device, int32 [B, T], caller-owned, or null to switch off) receives per frame the RcBranch bits of the
+// data-dependent decisions of the translation / contact / floor logic (net/sig_mp.py:185-225) taken by rc_forward_sequence.
+int rc_state_set_branch_log(rc_state* s, int32_t* log) {
+    RC_ARG(s);
+    s->branch_log = log;
     return RC_OK;
 }
 

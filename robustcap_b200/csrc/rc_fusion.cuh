@@ -90,6 +90,7 @@ struct rc_state {
     int* lists = nullptr;      // [NLISTS][B]
     int* counts = nullptr;     // [NLISTS]
     int* d_t = nullptr;        // device frame cursor (sequence mode)
+    int* branch_log = nullptr; // caller-owned device buffer [B, T] for the branch log, or null
     RcRowState* rows = nullptr;
     // cached CUDA graph of one steady-state frame
     cudaGraphExec_t graph = nullptr;
@@ -128,6 +129,8 @@ struct StepIO {
     long long sp, st;                      // per-stream strides
     const int* d_t;                        // frame cursor or nullptr (t = 0)
     int first_mode;                        // 0 never, 1 always, 2 only at t == 0
+    int* branch = nullptr;                 // optional debug log [B, T] of RcBranch bits (rc_state_set_branch_log)
+    long long sb = 0;                      // its per-stream stride
 };
 
 // stream.cu: one frame of ONE stream as a single cooperative kernel (all layers, grid-wide barriers instead of ~60 launches)

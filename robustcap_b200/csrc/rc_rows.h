@@ -31,6 +31,12 @@ enum RcFlag {
     RC_F_ACTIVE      = 256,    // stream still has frames (ragged batches)
 };
 
+// bits of the optional per-frame branch log (debug / parity tests: which data-dependent decision a frame took, :185-225)
+enum RcBranch {
+    RC_BR_CONTACT = 1, RC_BR_ARGMAX = 2, RC_BR_SNAP = 4, RC_BR_LERP = 8, RC_BR_FLOOR_ADD = 16, RC_BR_FLOOR_P1 = 32,
+    RC_BR_FLOOR_P0 = 64, RC_BR_INIT = 128,
+};
+
 struct RcModelConst {                 // SMPL constants the per-frame path needs (articulate/model.py:29-39)
     int parent[RC_NJ];                // parent[0] = -1
     int depth[RC_NJ];                 // tree depth of each joint (root 0); max_depth = deepest level
@@ -208,8 +214,9 @@ RC_HD void rc_floor_point(const float* pf, const float* tran, const float* g, fl
 // Translation / contact / floor state machine of one frame (sig_mp.py:185-227, 273): returns tran and updates the state.
 RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const float* pfoot, const float* y8, const float* vr,
                           const float* pc, const float* rcr, float conf, const float* gravity, const float* first_tran,
-                          float* tran_out) {
+                          float* tran_out, int* branch = nullptr) {
     const double c = (double)conf;
+    int br = 0;
     float ct0 = 1.f / (1.f + expf(-y8[0])), ct1 = 1.f / (1.f + expf(-y8[1]));           // sigmoid (:170)
     float cmax = fmaxf(ct0, ct1);
     int carg = (ct1 > ct0) ? 1 : 0;                                                      // argmax, first max wins
@@ -220,6 +227,7 @@ RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const 
         for (int r = 0; r < 3; ++r) v[r] = RC_DIV(RC_MUL(rv[r], 3.f), 60.f);             // * vel_scale / 60
     } else {
         for (int r = 0; r < 3; ++r) v[r] = RC_SUB(st->last_pfoot[carg * 3 + r], pfoot[carg * 3 + r]);   // :190
+        br |= RC_BR_CONTACT | (carg ? RC_BR_ARGMAX : 0);
     }
     float tran[3];
     for (int r = 0; r < 3; ++r) tran[r] = st->has_last ? RC_ADD(st->last_tran[r], v[r]) : v[r];       // :191-194
@@ -230,7 +238,9 @@ RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const 
         float d[3] = {RC_SUB(pc[0], tran[0]), RC_SUB(pc[1], tran[1]), RC_SUB(pc[2], tran[2])};
         if (rc_norm3(d) > cfg.dist_thr || cfg.tran_filter > 1) {
             for (int r = 0; r < 3; ++r) tran[r] = pc[r];
+            br |= RC_BR_SNAP;
         } else {
+            br |= RC_BR_LERP;
             double w = cfg.tran_filter * k;
             float wa = (float)(1.0 - w), wb = (float)w;
             for (int r = 0; r < 3; ++r) tran[r] = RC_ADD(RC_MUL(tran[r], wa), RC_MUL(pc[r], wb));
@@ -245,6 +255,7 @@ RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const 
         const float* p = (rc_norm3(p0) < rc_norm3(p1)) ? p1 : p0;
         for (int r = 0; r < 3; ++r) st->floor_y[st->floor_n][r] = p[r];
         st->floor_n += 1;
+        br |= RC_BR_FLOOR_ADD;
     }
     if (cfg.use_flat_floor && st->floor_n > 10 && cmax > cfg.contact_thr) {             // :215-221
         float p0[3], p1[3], m[3], d0[3], d1[3];
@@ -258,8 +269,10 @@ RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const 
         }
         if (rc_norm3(p0) < rc_norm3(p1) && rc_norm3(d1) < cfg.height_thr) {
             for (int r = 0; r < 3; ++r) tran[r] = RC_ADD(tran[r], d1[r]);
+            br |= RC_BR_FLOOR_P1;
         } else if (rc_norm3(d0) < cfg.height_thr) {
             for (int r = 0; r < 3; ++r) tran[r] = RC_ADD(tran[r], d0[r]);
+            br |= RC_BR_FLOOR_P0;
         }
     }
     if (ft) { for (int r = 0; r < 3; ++r) tran[r] = first_tran[r]; }                     // :222-225
@@ -268,7 +281,7 @@ RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const 
     for (int e = 0; e < 6; ++e) st->last_pfoot[e] = pfoot[e];                            // :227
     for (int r = 0; r < 3; ++r) { st->last_tran[r] = tran[r]; tran_out[r] = tran[r]; }   // :273
     st->has_last = 1;
-
+    if (branch) *branch = br;
 }
 
 // Inputs: y7[144] (6D global pose), y8[2] (contact logits), vr[3] (rnn3), pc[3] (rnn6 early result, valid when
@@ -278,7 +291,7 @@ RC_HD void rc_tran_update(const RcNetCfg& cfg, RcRowState* st, int flags, const 
 RC_HD int rc_kin_row(const RcNetCfg& cfg, const RcModelConst& M, RcRowState* st, int flags, const float* y7,
                      const float* y8, const float* vr, const float* pc, const float* rcr, float conf,
                      const float* gravity, const float* first_tran, float* pose, float* tran_out, float* x4,
-                     float* x6) {
+                     float* x6, int* branch = nullptr) {
     float G[RC_NJ][9];
     for (int i = 0; i < RC_NJ; ++i) rc_r6d_to_mat(y7 + i * 6, G[i]);                   // :173
     for (int e = 0; e < 9; ++e) pose[e] = rcr[e];                                        // pose[0] = Rcr (:175)
@@ -301,7 +314,9 @@ RC_HD int rc_kin_row(const RcNetCfg& cfg, const RcModelConst& M, RcRowState* st,
             pfoot[f * 3 + j] = jp[10 + f][0] * rcr[j * 3 + 0] + jp[10 + f][1] * rcr[j * 3 + 1] + jp[10 + f][2] * rcr[j * 3 + 2];
 
     float tran[3];
-    rc_tran_update(cfg, st, flags, pfoot, y8, vr, pc, rcr, conf, gravity, first_tran, tran);
+    int br = 0;
+    rc_tran_update(cfg, st, flags, pfoot, y8, vr, pc, rcr, conf, gravity, first_tran, tran, &br);
+    if (branch) *branch = br | (need_init ? RC_BR_INIT : 0);
     for (int r = 0; r < 3; ++r) tran_out[r] = tran[r];
 
     // :228-242 mesh FK -> synthetic key points; live mode recomputes every (freq+1)-th frame only

@@ -24,7 +24,7 @@ __device__ __forceinline__ int rc_kin_warp(const RcNetCfg& cfg, const RcModelCon
                                            const float* __restrict__ gy7, const float* y8, const float* vr, const float* pc,
                                            const float* rcr, float conf, const float* gravity, const float* first_tran,
                                            float* __restrict__ gpose, float* __restrict__ gtran, float* __restrict__ x4,
-                                           float* __restrict__ x6, int lane) {
+                                           float* __restrict__ x6, int lane, int* branch = nullptr) {
     for (int e = lane; e < 144; e += 32) S.y7[e] = gy7[e];
     {   // state: struct copy through 4-byte words, coalesced
         const int* src = reinterpret_cast<const int*>(gst);
@@ -54,7 +54,9 @@ __device__ __forceinline__ int rc_kin_warp(const RcNetCfg& cfg, const RcModelCon
             for (int j = 0; j < 3; ++j)
                 pfoot[f * 3 + j] = S.jp[10 + f][0] * rcr[j * 3 + 0] + S.jp[10 + f][1] * rcr[j * 3 + 1] + S.jp[10 + f][2] * rcr[j * 3 + 2];
         float tran[3];
-        rc_tran_update(cfg, &S.st, flags, pfoot, y8, vr, pc, rcr, conf, gravity, first_tran, tran);
+        int br = 0;
+        rc_tran_update(cfg, &S.st, flags, pfoot, y8, vr, pc, rcr, conf, gravity, first_tran, tran, &br);
+        if (branch) *branch = br | (need_init ? RC_BR_INIT : 0);
         S.tran[0] = tran[0]; S.tran[1] = tran[1]; S.tran[2] = tran[2];
     }
     need_init = __shfl_sync(0xffffffffu, need_init, 0);

@@ -201,7 +201,7 @@ class Net(torch.nn.Module):
 
     @torch.no_grad()
     def forward_offline(self, j2dc, accc, oric, first_tran=None, first_frame=False, lengths=None, use_graph=None,
-                        first_tran_mask=None, out=None, gravity=None):
+                        first_tran_mask=None, out=None, gravity=None, branch_log=None):
         r"""``reset_states()`` then ``forward_online`` over every frame (evaluate.py:75-85, 93), natively batched.
 
         j2dc [T,33,3] or [B,T,33,3]; accc [..,T,6,3]; oric [..,T,6,3,3].  ``first_tran`` ([3] or [B,3]) and
@@ -236,6 +236,9 @@ class Net(torch.nn.Module):
         any_ff = int(bool((flags & 1).any()))
         use_flags = bool(flags.any())
         ln = None if lengths is None else torch.as_tensor(lengths).to('cpu', torch.int32).reshape(B).contiguous()
+        if branch_log is not None:     # debug / parity aid: int32 [B, T] on the device, receives the RcBranch bits per frame
+            assert not on_cpu and branch_log.is_cuda and branch_log.dtype == torch.int32 and branch_log.numel() == B * T
+        _lib.check(lib.rc_state_set_branch_log(st, None if branch_log is None else branch_log.data_ptr()))
         if out is not None:            # caller-provided result buffers (e.g. pinned host memory), contiguous float32
             pose, tran = out[0].view(B, T, 24, 3, 3), out[1].view(B, T, 3)
             assert pose.is_cuda == (not on_cpu) and pose.dtype == torch.float32
