@@ -111,10 +111,17 @@ int rc_net_set_config(rc_net* n, const rc_net_config* cfg);
 int rc_net_set_tensor(rc_net* n, const char* key, const float* h_data, int64_t numel);
 int rc_net_finalize(rc_net* n);
 int64_t rc_net_weight_bytes(const rc_net* n);     /* bytes of packed per-frame weights resident in HBM */
-/* Batched (B > 8) GEMM back end: 2 (default) = persistent grouped tcgen05 kernel on CTA pairs, one launch per phase of the frame
- * (phase_tc.cu); 1 = tcgen05, one launch per layer (gemm_tc.cu); 0 = fp32 SIMT tiles.  Both tcgen05 paths use split-fp16
- * operands with fp32-level accuracy.  B <= 8 always uses the weight-streaming GEMV kernels. */
+/* Batched (B > 8) back end: 3 = persistent SEQUENCE kernel (seq_tc.cu): after a few warm-up frames all remaining frames of
+ * rc_forward_sequence run in ONE launch — GEMM tiles (tcgen05) and the per-frame row logic (prep / joint blend / kinematics +
+ * translation state machine / init_net) as items of one dependency queue, resident CTAs, no kernel boundary per frame;
+ * 2 (default) = persistent grouped tcgen05 kernel, one launch per phase of the frame (phase_tc.cu), which hands small batches
+ * (<= 128 streams, see rc_net_set_seq_options) to the sequence kernel; 1 = tcgen05, one launch per layer (gemm_tc.cu); 0 = fp32 SIMT
+ * tiles.  All tcgen05 paths use split-fp16 operands with fp32-level accuracy.  B <= 8 always uses the weight-streaming GEMV kernels. */
 int rc_net_set_gemm_mode(rc_net* n, int mode);
+/* Sequence-kernel policy: in gemm mode 2, batches of at most auto_max_streams streams (default 128 = one row block; 0 = never) use
+ * the sequence kernel; the first warm_frames frames (default 16) of every sequence go through the multi-launch path, which runs the
+ * init_net re-seeds (net/sig_mp.py:178-183, mostly in the first frames) on the tensor cores.  Negative / zero values keep the setting. */
+int rc_net_set_seq_options(rc_net* n, int32_t auto_max_streams, int32_t warm_frames);
 
 int rc_state_create(rc_state** out, const rc_net* net, int32_t b);
 void rc_state_destroy(rc_state* s);
@@ -241,6 +248,12 @@ int rc_state_debug_output(rc_state* s, int which, float* h_out, void* stream);
  * (:203), 16 floor sample stored (:208-214), 32 / 64 floor snap through the far / near foot (:217-221), 128 rnn2 re-seeded by
  * init_net (:178-183).  Parity tests report the first frame where the CUDA path and the oracle disagree and which bit flipped. */
 int rc_state_set_branch_log(rc_state* s, int32_t* d_log);
+
+/* Debug tap of the persistent sequence kernel (gemm mode 3; environment RC_SEQ_STATS=1 switches the counters on): per job of the
+ * frame's work queue, h_out[4 j + {0: work items run, 1: clocks spent waiting for state / hazard dependencies, 2: clocks waiting for
+ * the producer of the x half of an LSTM operand, 3: items skipped because no stream of the block needed them}] of the last
+ * rc_forward_sequence call; returns the number of jobs written (<= max_jobs). */
+int rc_state_debug_seq_stats(rc_state* s, long long* h_out, int32_t max_jobs);
 
 /* Debug tap of the persistent grouped GEMM kernel (gemm mode 2): enable != 0 makes every later launch record, per tile, 16 int64
  * {cta<<32|job<<16|row block<<8|column tile, clock64 at: grab, dependency met, first MMA, last commit, accumulators seen by the

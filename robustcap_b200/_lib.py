@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO_PATH = os.path.join(CSRC, 'librobustcap_b200.so')
-SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'phase_tc.cu', 'stream.cu', 'metrics.cu', 'pipeline.cu']
+SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'phase_tc.cu', 'seq_tc.cu', 'stream.cu', 'metrics.cu', 'pipeline.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 
@@ -112,6 +112,8 @@ _SIGS = {
     'rc_live_format_pose': (i32, [vp, vp, ctypes.c_char_p, i32]),
     'rc_live_parse_imu_packet': (i32, [ctypes.c_char_p, i32, i32, vp, vp, vp]),
     'rc_state_set_branch_log': (i32, [vp, vp]),
+    'rc_net_set_seq_options': (i32, [vp, i32, i32]),
+    'rc_state_debug_seq_stats': (i32, [vp, vp, i32]),
     'rc_profile_enable': (i32, [vp, i32]),
     'rc_profile_collect': (i32, [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double)]),
 }

@@ -22,6 +22,7 @@
 #include "rc_pack.h"
 #include "rc_tc.cuh"
 #include "rc_fusion.cuh"
+#include "rc_seq.cuh"
 
 namespace {
 
@@ -603,7 +604,7 @@ int grouped_tail(rc_state* s, bool advance, void* stream) {
     return RC_OK;
 }
 
-bool grouped_path(const rc_state* s) { return s->net->gemm_mode == 2 && s->ph_ready && s->B > 8; }
+bool grouped_path(const rc_state* s) { return s->net->gemm_mode >= 2 && s->ph_ready && s->B > 8; }
 
 int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advance, void* stream) {
     const rc_net* n = s->net;
@@ -734,6 +735,8 @@ int rc_net_create(rc_net** out, const rc_model* model, const rc_net_config* cfg)
     rc_net_config def;
     rc_net_default_config(&def, 0);
     apply_cfg(n, cfg ? cfg : &def);
+    if (getenv("RC_SEQ_AUTO_B")) n->seq_auto_B = atoi(getenv("RC_SEQ_AUTO_B"));      // A/B switches for bench runs
+    if (getenv("RC_SEQ_WARM")) n->seq_warm = std::max(1, atoi(getenv("RC_SEQ_WARM")));
     *out = n;
     return RC_OK;
 }
@@ -797,8 +800,15 @@ int rc_net_finalize(rc_net* n) {
 
 int64_t rc_net_weight_bytes(const rc_net* n) { return n ? n->weight_bytes : 0; }
 
+int rc_net_set_seq_options(rc_net* n, int auto_max_streams, int warm_frames) {
+    RC_ARG(n);
+    if (auto_max_streams >= 0) n->seq_auto_B = auto_max_streams;
+    if (warm_frames >= 1) n->seq_warm = warm_frames;
+    return RC_OK;
+}
+
 int rc_net_set_gemm_mode(rc_net* n, int mode) {
-    RC_ARG(n && (mode == 0 || mode == 1 || mode == 2));
+    RC_ARG(n && mode >= 0 && mode <= 3);
     if (mode >= 1 && !n->tc_ready) { rc_set_error("tensor-core path unavailable (tensor maps could not be created)"); return RC_ERR_STATE; }
     n->gemm_mode = mode;
     return RC_OK;
@@ -872,6 +882,7 @@ void rc_state_destroy(rc_state* s) {
     if (s->on_graph) cudaGraphExecDestroy(s->on_graph);
     cudaFree(s->sk_bar); cudaFree(s->sk_rows);
     cudaFree(s->on_din); cudaFree(s->on_dout); cudaFreeHost(s->on_hin); cudaFreeHost(s->on_hout);
+    rc_seq_destroy(s);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     if (s->side) cudaStreamDestroy(s->side);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
@@ -1010,6 +1021,22 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
     // side stream even when the list is empty, longer than prep + lists, so nothing was gained: 525 vs 527 us per frame.)
     RC_TRY(enqueue_step(s, io, any_first_frame, true, stream));
     if (T == 1) return RC_OK;
+    // Sequence kernel: forced by gemm mode 3; chosen automatically in the default mode 2 for small shards (<= 128 streams = one
+    // row block, e.g. the 8-GPU split of 1024 sequences), where a frame is bound by its dependency chain and the 13 launch
+    // boundaries of the multi-launch path cost more than the masked (uncompacted) passes of the sequence kernel.
+    const bool want_seq = s->net->gemm_mode == 3 || (s->net->gemm_mode == 2 && s->B <= s->net->seq_auto_B && T >= 3 * s->net->seq_warm);
+    if (want_seq && grouped_path(s) && rc_seq_supported(s)) {
+        // frames 1 .. T-1 in ONE launch: persistent sequence kernel (tile width 64 for small shards, where the frame is bound by the
+        // depth of its dependency chain; 128 where it is bound by the tensor pipe)
+        static const int bn_env = getenv("RC_SEQ_BN") ? atoi(getenv("RC_SEQ_BN")) : 0;
+        const int bn = (bn_env == 64 || bn_env == 128) ? bn_env : (s->B <= 256 ? 64 : 128);
+        // The first frames of a sequence are where most streams reach c >= hi for the first time and re-seed rnn2 through init_net
+        // (:178-183); that MLP runs on the tensor cores in the multi-launch path but only as a (correct, slow) per-stream row job
+        // inside the sequence kernel, so the sequence kernel takes over after a few frames.
+        const int t0 = std::max(1, std::min(s->net->seq_warm, T - 1));
+        for (int t = 1; t < t0; ++t) RC_TRY(enqueue_step(s, io, 0, true, stream));
+        return rc_seq_run(s, io, T, t0, bn, stream);
+    }
     if (!use_graph) {
         for (int t = 1; t < T; ++t) RC_TRY(enqueue_step(s, io, 0, true, stream));
         g_tl.report(11);
@@ -1119,6 +1146,11 @@ int rc_state_set_branch_log(rc_state* s, int32_t* log) {
     return RC_OK;
 }
 
+int rc_state_debug_seq_stats(rc_state* s, long long* out, int32_t max_jobs) {
+    if (!s || !out) return 0;
+    return rc_seq_stats(s, out, max_jobs);
+}
+
 int rc_profile_enable(rc_state* s, int on) {
     RC_ARG(s);
     s->prof_on = on;
@@ -1138,7 +1170,7 @@ int rc_profile_collect(rc_state* s, double* total_ms, int64_t* launches, double*
     *total_ms = tot;
     *launches = (int64_t)(s->prof_used / 2);
     if (flop_per_row) {
-        if (s->net->gemm_mode == 2 && s->ph_ready && s->B > 8) {
+        if (s->net->gemm_mode >= 2 && s->ph_ready && s->B > 8) {
             // grouped kernel: the launches of one frame together run the whole LSTM stack of one stream once (SURVEY.md 8d:
             // 60 689 920 MAC = 121.4 MFLOP per stream-frame)
             double mac = 0;
@@ -1190,6 +1222,8 @@ int rc_state_debug_output(rc_state* s, int which, float* out, void* stream) {
         case 6: src = s->Y6; ld = 4; w = 3; break;
         case 7: src = s->Y7; ld = 144; w = 144; break;
         case 8: src = s->Y8; ld = 4; w = 2; break;
+        case 70: src = s->X7 + 72; ld = RC_K7; w = 69; break;                 // blended joints, multi-launch path
+        case 71: src = rc_seq_debug_j3dr(s); ld = 72; w = 69; if (!src) { rc_set_error("sequence kernel has not run"); return RC_ERR_STATE; } break;
         default: rc_set_error("rc_state_debug_output: which=%d", which); return RC_ERR_ARG;
     }
     RC_CUDA(cudaMemcpy2DAsync(out, (size_t)w * 4, src, (size_t)ld * 4, (size_t)w * 4, (size_t)s->B, cudaMemcpyDeviceToHost, (cudaStream_t)stream));

@@ -48,13 +48,21 @@ struct rc_net {
     int64_t weight_bytes = 0;
     std::vector<void*> allocs;
     int gemm_mode = 2;          // 0 = fp32 SIMT tiles, 1 = tcgen05 split-fp16, one launch per layer, 2 = tcgen05 persistent
-                                // grouped kernel, one launch per phase of the frame (batches > 8 streams)
+                                // grouped kernel, one launch per phase of the frame (batches > 8 streams), 3 = persistent SEQUENCE
+                                // kernel: frames 1 .. T-1 of rc_forward_sequence in one launch (seq_tc.cu), mode 2 elsewhere
     bool tc_ready = false;
+    // sequence kernel (seq_tc.cu): in mode 2 it is chosen automatically for batches of at most seq_auto_B streams; the first
+    // seq_warm frames of a sequence (where most streams re-seed rnn2 through init_net) always go through the multi-launch path
+    int seq_auto_B = 128;
+    int seq_warm = 16;
     int cfg_version = 0;        // bumped by rc_net_set_config: captured CUDA graphs bake the config into kernel arguments
 };
 
+struct RcSeq;                          // persistent sequence kernel (seq_tc.cu)
+
 struct rc_state {
     const rc_net* net = nullptr;
+    RcSeq* seq = nullptr;
     int B = 0;
     bool fresh = true;                 // first reset after creation also zeroes the fields reset_states leaves alone
     std::vector<void*> allocs;

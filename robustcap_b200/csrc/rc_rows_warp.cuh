@@ -5,6 +5,29 @@
 #pragma once
 #include "rc_rows.h"
 
+// rc_normalise_kp (sig_mp.py:150-152 / 268-270) across a warp: lanes = key points (lane 0 also takes key point 32).  max / min do not
+// depend on the order and every quotient / difference is the scalar function's, so the result is bit-identical to rc_normalise_kp.
+__device__ __forceinline__ void rc_normalise_kp_warp(const float* kp, float* out, int lane) {
+    float u = kp[lane * 3], v = kp[lane * 3 + 1];
+    float umax = u, umin = u, vmax = v, vmin = v;
+    if (lane == 0) {
+        const float u2 = kp[32 * 3], v2 = kp[32 * 3 + 1];
+        umax = fmaxf(umax, u2); umin = fminf(umin, u2); vmax = fmaxf(vmax, v2); vmin = fminf(vmin, v2);
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, s)); umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, s));
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, s)); vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, s));
+    }
+    const float sc = fmaxf(RC_SUB(umax, umin), RC_SUB(vmax, vmin));
+    const float rx = RC_DIV(kp[23 * 3], sc), ry = RC_DIV(kp[23 * 3 + 1], sc);
+    for (int i = lane; i < RC_NKP; i += 32) {
+        float x = RC_DIV(kp[i * 3], sc), y = RC_DIV(kp[i * 3 + 1], sc);
+        if (i != 23) { x = RC_SUB(x, rx); y = RC_SUB(y, ry); }
+        out[i * 3] = x; out[i * 3 + 1] = y; out[i * 3 + 2] = kp[i * 3 + 2];
+    }
+}
+
 struct RcKinWarpSmem {
     float y7[144];
     float G[RC_NJ][9];
@@ -112,7 +135,7 @@ __device__ __forceinline__ int rc_kin_warp(const RcNetCfg& cfg, const RcModelCon
             __syncwarp();
             for (int e = lane; e < 99; e += 32) x6[72 + e] = S.syn[e];
             for (int e = lane; e < 69; e += 32) x6[171 + e] = RC_SUB(S.joint[1 + e / 3][e % 3], S.joint[0][e % 3]);
-            if (lane == 0) rc_normalise_kp(S.syn, x4 + 72);
+            rc_normalise_kp_warp(S.syn, x4 + 72, lane);
         }
     } else if (!do_fk) {
         if (lane == 0) S.st.vision_count -= 1;
@@ -153,7 +176,8 @@ __device__ __forceinline__ int rc_prep_warp(const RcNetCfg& cfg, int vision_coun
     if (lane < 9) rcr[lane] = R[lane];
     if (lane < 6) rc_vec_mat3(S.acc + lane * 3, R, S.xr + lane * 3);                               // accr = accc @ Rcr  (:142)
     else if (lane < 12) rc_mat3_tmul(R, S.ori + (lane - 6) * 9, S.xr + 18 + (lane - 6) * 9);       // orir = Rcr^T @ oric (:143)
-    if ((f & RC_F_HI) && lane == 12) rc_normalise_kp(S.kp, S.kpn);                                 // :150-152
+    __syncwarp();
+    if (f & RC_F_HI) rc_normalise_kp_warp(S.kp, S.kpn, lane);                                     // :150-152
     __syncwarp();
     for (int e = lane; e < 72; e += 32) {
         const float v = S.xr[e];

@@ -153,11 +153,18 @@ class Net(torch.nn.Module):
         return out
 
     def set_gemm_mode(self, mode):
-        """Batched (B > 8) GEMM back end: 2 = persistent grouped tcgen05 kernel, one launch per phase of the frame (default),
-        1 = tcgen05 one launch per layer, 0 = fp32 SIMT tiles.  Both tcgen05 paths use split-fp16 operands (fp32-accurate)."""
+        """Batched (B > 8) back end: 3 = persistent SEQUENCE kernel (frames 1..T-1 of ``forward_offline`` in one launch: GEMM tiles
+        and the per-frame row logic in one dependency queue), 2 = persistent grouped tcgen05 kernel, one launch per phase of the
+        frame, 1 = tcgen05 one launch per layer, 0 = fp32 SIMT tiles.  All tcgen05 paths use split-fp16 operands (fp32-accurate)."""
         self._ensure_native()
         _lib.check(_lib.load().rc_net_set_gemm_mode(self._net, int(mode)))
         self._gemm_mode = int(mode)
+
+    def set_seq_options(self, auto_max_streams=-1, warm_frames=0):
+        """Policy of the persistent sequence kernel: batches of at most ``auto_max_streams`` streams use it in the default mode
+        (0 = never), after ``warm_frames`` frames through the multi-launch path.  Negative / zero keep the current value."""
+        self._ensure_native()
+        _lib.check(_lib.load().rc_net_set_seq_options(self._net, int(auto_max_streams), int(warm_frames)))
 
     def weight_bytes(self):
         self._ensure_native()
