@@ -5,10 +5,11 @@
   python bench.py --impl reference ...                   the reference's CPU implementation of the same path
 
 Workload (BASELINE.json configs[2]): offline evaluation of `--seqs` (1024) independent sequences x `--frames` (300)
-frames per GPU, synthetic 6-IMU + 33x3 key points with per-frame confidence U(0.6, 1.0) (all three branches of
-net/sig_mp.py:149-167), random-init weights.  One "step" = one forward_offline pass over that batch.  Multi-GPU:
-sequences are sharded by rank (weak scaling: every rank gets `--seqs` sequences), the only collective is the final
-NCCL gather of pose/tran to rank 0, inside the timed region.
+frames, synthetic 6-IMU + 33x3 key points with per-frame confidence U(0.6, 1.0) (all three branches of
+net/sig_mp.py:149-167), random-init weights.  One "step" = one forward_offline pass over the batch.  Multi-GPU
+(`--scaling strong`, default, the configuration BASELINE names): the 1024 sequences are sharded over the N ranks
+(contiguous blocks, `robustcap_b200.distributed`), no data-path collective, one NCCL gather of [pose | tran] to rank 0
+inside the timed region.  `--scaling weak` gives every rank `--seqs` sequences instead.
 
   value  frames/s, whole job, inputs already resident in HBM (device-timed with CUDA events, max over ranks)
   e2e    the same pass through the host-buffer C-ABI entry point (pinned host inputs -> H2D -> kernels -> D2H)
@@ -42,7 +43,10 @@ def parse():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--seqs', type=int, default=1024, help='sequences per GPU')
+    ap.add_argument('--seqs', type=int, default=1024, help='sequences of the job (strong scaling) / per GPU (weak scaling)')
+    ap.add_argument('--scaling', default='strong', choices=['strong', 'weak'])
+    ap.add_argument('--no-occlusion', action='store_true', help='skip the occlusion-workload line (BASELINE configs[4])')
+    ap.add_argument('--no-smplify', action='store_true', help='skip the fusion + FK + SMPLify line (BASELINE configs[3])')
     ap.add_argument('--frames', type=int, default=300)
     ap.add_argument('--conf', default='mixed')
     ap.add_argument('--cpu-frames', type=int, default=240, help='frames of the bounded CPU-baseline sample')
@@ -173,35 +177,140 @@ def cpu_reference_rate(sd, assets, frames, conf, impl='aten', warm=10):
             'ms_per_frame_p50': 1e3 * statistics.median(per)}
 
 
+def workload_config(args, world, B_rank):
+    """The `config` object of the JSON line — identical in both arms (the driver compares them)."""
+    if args.scaling == 'strong':
+        wl = ('offline_eval %d seq x %d frames sharded over %d GPU(s) (BASELINE configs[2]; configs[1] = the same net streaming at B=1, '
+              'reported under "streaming")' % (args.seqs, args.frames, world))
+    else:
+        wl = 'offline_eval %d seq x %d frames per GPU, weak scaling (BASELINE configs[2] per GPU)' % (args.seqs, args.frames)
+    return {'workload': wl, 'conf': args.conf, 'weights': 'random-init seed 0 (contact variant)'}
+
+
+# ---- the reference arm ---------------------------------------------------------------------------------------------------------------
+REF_ARCHIVE = os.path.join(REPO, 'baseline', '_ref', 'reference_src.tar.gz')
+
+
+def load_real_reference():
+    """The UNMODIFIED reference (its .py sources, archived by __graft_entry__.build() from /root/reference into the git-ignored
+    baseline/_ref/, which travels to the GPU box), imported with stub modules for the viz / training deps and the seeded
+    synthetic assets — the recipe of tests/golden/make_golden.py.  Returns its `Net` class, or None when the archive is absent."""
+    if not os.path.exists(REF_ARCHIVE):
+        return None
+    import tarfile
+    import types
+    import warnings
+    from robustcap_b200 import synthetic
+    dst = tempfile.mkdtemp(prefix='robustcap_ref_')
+    with tarfile.open(REF_ARCHIVE) as tf:
+        tf.extractall(dst)
+    for name in ('trimesh', 'pyrender', 'smplx', 'wandb'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['smplx'].SMPL = object
+    thop = types.ModuleType('thop')
+    thop.clever_format = lambda *a, **k: ''
+    sys.modules['thop'] = thop
+    # this arm times the reference's CPU implementation on the host cores: its modules pick `cuda` at import when one is visible
+    os.environ['CUDA_VISIBLE_DEVICES'] = ''
+    torch.cuda.is_available = lambda: False
+    root = synthetic.default_asset_root()
+    synthetic.write_assets(root, 0)
+    os.chdir(root)                                  # the reference opens models/SMPL_male.pkl relative to the CWD at import
+    sys.path.insert(0, os.path.join(dst, 'reference'))
+    warnings.filterwarnings('ignore')
+    from net.sig_mp import Net as RefNet            # noqa: E402  (the reference's own module)
+    return RefNet
+
+
+def reference_pass(net, inp, frames):
+    """evaluate.py:75-85, 93 on one sequence: the reference's own per-frame loop."""
+    with torch.no_grad():
+        for t in range(frames):
+            kw = {'first_tran': torch.tensor([0., 0., 4.])} if t == 0 else {}
+            net.forward_online(inp['j2dc'][0, t], inp['accc'][0, t], inp['oric'][0, t], **kw)
+        net.reset_states()
+
+
+def best_threads(fn):
+    """Thread count that maximises the throughput of a GEMV-sized CPU loop on this host (the default of one thread per core —
+    128+ on the B200 box — is far slower than a few threads)."""
+    ncpu = os.cpu_count() or 1
+    best, best_t = 1, None
+    for n in sorted({1, 2, 4, 8, 16, 32, ncpu}):
+        if n > ncpu:
+            continue
+        torch.set_num_threads(n)
+        fn()
+        t0 = time.perf_counter()
+        fn()
+        t = time.perf_counter() - t0
+        if best_t is None or t < best_t:
+            best, best_t = n, t
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
     from robustcap_b200 import synthetic
     assets = synthetic.write_assets(synthetic.default_asset_root(), 0)
     sd = synthetic.make_state_dict(0, 'contact')
-    o = make_cpu_reference(sd, assets, 'aten')
-    frames = 60
-    inp = synthetic.make_inputs(1, frames, seed=99, conf=args.conf)
+    frames = args.frames
+    inp = synthetic.make_inputs(1, frames, seed=1000, conf=args.conf)
+    RefNet = None
+    try:
+        RefNet = load_real_reference()
+    except Exception as e:                           # fall back to the port, say why
+        print('reference import failed (%s: %s); timing the oracle port instead' % (type(e).__name__, e), file=sys.stderr)
+    if RefNet is not None:
+        RefNet.gravityc = inp['gravity'].clone()
+        net = RefNet()
+        net.load_state_dict(sd)
+        net.eval()
+        probe = {k: (v[:, :8] if v.dim() > 1 else v) for k, v in inp.items()}
+        best_threads(lambda: reference_pass(net, probe, 8))
+        run = lambda: reference_pass(net, inp, frames)
+        kind = 'reference'
+        what = ('per step: ONE full sequence of %d frames through the unmodified reference (net/sig_mp.py Net.forward_online per frame + '
+                'reset_states, evaluate.py:75-85,93) on the host cores, same weights / synthetic assets / inputs as rank 0 sequence 0' % frames)
+    else:
+        o = make_cpu_reference(sd, assets, 'aten')
+        run = lambda: cpu_reference_pass(o, inp, frames)
+        kind = 'port'
+        what = ('per step: ONE full sequence of %d frames through the oracle port (oracle/fusion.py with torch.nn.LSTM, the ATen back end '
+                'the reference runs on); baseline/_ref/reference_src.tar.gz was not found, so the reference itself could not be imported' % frames)
     times = []
     for i in range(max(args.warmup, 1) + args.steps):
         t0 = time.perf_counter()
-        cpu_reference_pass(o, inp, frames)
+        run()
         if i >= max(args.warmup, 1):
             times.append(time.perf_counter() - t0)
     ms = 1e3 * sum(times) / len(times)
     value = frames / (ms / 1e3)
-    line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+    line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': max(args.warmup, 1),
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': 'offline_eval %d seq x %d frames per GPU (BASELINE configs[2])' % (args.seqs, args.frames),
-                       'conf': args.conf, 'weights': 'random-init seed 0 (contact variant)'},
-            'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': 'per step: 1 sequence x %d frames of the same workload (oracle/fusion.py, torch.nn.LSTM as the '
-                                       'reference); the reference processes sequences one after another, so frames/s does not depend on '
-                                       'the number of sequences' % frames},
+            'config': workload_config(args, world, None),
+            'cpu_baseline': {'value': value, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'host_cpus': os.cpu_count(), 'kind': kind,
+                             'sample': what + '; the reference processes sequences one after another (batch 1, stateful), so its frames/s does '
+                                              'not depend on how many sequences the job has'},
             'e2e': {'value': value, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)
+
+
+def timed_passes(fn, n, barrier):
+    """n calls of fn between two CUDA events (device time, ms per call)."""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1) / n
 
 
 def main():
@@ -220,6 +329,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
     from robustcap_b200 import _lib, synthetic
+    from robustcap_b200 import distributed as rdist
     if rank == 0:
         _lib.build()
         synthetic.write_assets(synthetic.default_asset_root(), 0)
@@ -228,31 +338,39 @@ def main():
     lib = _lib.load()
     net, sd, assets = build_net()
     net.set_gemm_mode(args.gemm_mode)
-    B, T = args.seqs, args.frames
+    T = args.frames
+    if args.scaling == 'strong':
+        lo, hi = rdist.shard_bounds(args.seqs, rank, world)
+        total_seqs = args.seqs
+    else:
+        lo, hi = 0, args.seqs
+        total_seqs = args.seqs * world
+    B = hi - lo                                     # this rank's shard
+    counts = [rdist.shard_bounds(args.seqs, r, world)[1] - rdist.shard_bounds(args.seqs, r, world)[0] for r in range(world)] \
+        if args.scaling == 'strong' else [args.seqs] * world
     inp = synthetic.make_inputs(B, T, seed=1000 + rank, conf=args.conf)
     type(net).gravityc = inp['gravity'].clone()
     j, a, o = inp['j2dc'].to(dev), inp['accc'].to(dev), inp['oric'].to(dev)
     ft = torch.tensor([0., 0., 4.], device=dev)
-    gather_pose = gather_tran = None
+    res = rdist.ShardedResult(B, T, dev)            # one flat [pose | tran] buffer per rank: ONE collective for both
+    recv = None
     if world > 1 and rank == 0:
-        gather_pose = [torch.empty(B, T, 24, 3, 3, device=dev) for _ in range(world)]
-        gather_tran = [torch.empty(B, T, 3, device=dev) for _ in range(world)]
+        recv = [torch.empty(c * T * 219, device=dev) for c in counts]
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    out_p = torch.empty(B, T, 24, 3, 3, device=dev)
-    out_t = torch.empty(B, T, 3, device=dev)
-
-    def step(graph=True):
-        # graph=True is the default behaviour of Net.forward_offline (frames 1..T-1 replay one captured CUDA graph)
-        pose, tran = net.forward_offline(j, a, o, first_tran=ft, use_graph=graph, out=(out_p, out_t))
+    def step(graph=True, jj=j, aa=a, oo=o):
+        # graph=True is the default behaviour of Net.forward_offline (multi-launch path: frames 1..T-1 replay one captured CUDA
+        # graph; shards of <= 128 sequences: the persistent sequence kernel takes over after the warm-up frames)
+        net.forward_offline(jj, aa, oo, first_tran=ft, use_graph=graph, out=(res.pose, res.tran))
         if dist is not None:
-            dist.gather(pose, gather_pose, dst=0)
-            dist.gather(tran, gather_tran, dst=0)
-        return pose, tran
+            if len(set(counts)) == 1:
+                dist.gather(res.flat, recv if rank == 0 else None, dst=0)
+            else:
+                rdist.gather_flat(res, total_seqs, 0, None, recv)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -261,14 +379,7 @@ def main():
     clocks = ClockSampler(local)
     clocks.start()
     launches0 = lib.rc_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_step = timed_passes(step, args.steps, barrier)
     launches = lib.rc_launch_count() - launches0
     clk = clocks.stop()
     # Roofline pass: the same K steps once more with plain stream launches, so that CUDA events can sit right around every launch
@@ -277,23 +388,32 @@ def main():
     step(False)
     barrier()
     _lib.check(lib.rc_profile_enable(st, 1))
-    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    for _ in range(args.steps):
-        step(False)
-    r1.record()
-    barrier()
-    roof_ms_total = r0.elapsed_time(r1)
+    roof_ms = timed_passes(lambda: step(False), args.steps, barrier)
     tot_ms, nl, fpr = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
     _lib.check(lib.rc_profile_collect(st, ctypes.byref(tot_ms), ctypes.byref(nl), ctypes.byref(fpr)))
     _lib.check(lib.rc_profile_enable(st, 0))
-    t_ms = torch.tensor([ms_total], device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_total = float(t_ms.item())
-    ms_step = ms_total / args.steps
-    frames_step = B * T * world
+
+    def allmax(x):
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_step = allmax(ms_step)
+    frames_step = total_seqs * T
     value = frames_step / (ms_step / 1e3)
+
+    # ---- occlusion workload (BASELINE configs[4]): key-point confidence 0 on 50 % of the frames -> IMU-only branch + vision updater ----
+    occ = None
+    if not args.no_occlusion:
+        oi = synthetic.make_inputs(B, T, seed=2000 + rank, conf='occluded')
+        oj, oa, oo = oi['j2dc'].to(dev), oi['accc'].to(dev), oi['oric'].to(dev)
+        for _ in range(2):
+            step(True, oj, oa, oo)
+        occ_ms = allmax(timed_passes(lambda: step(True, oj, oa, oo), max(2, min(args.steps, 3)), barrier))
+        occ = {'conf': 'occluded: confidence 0 on a seeded random 50 % of the frames, U(0.9, 1) elsewhere', 'ms_per_step': occ_ms,
+               'value': frames_step / (occ_ms / 1e3), 'unit': 'frames/s'}
+        del oj, oa, oo
 
     # ---- end-to-end through the host-buffer C-ABI entry point (pinned buffers) --------------------------------
     pin = lambda x: x.contiguous().pin_memory()
@@ -309,13 +429,10 @@ def main():
     for _ in range(reps):
         net.forward_offline(hj, ha, ho, first_tran=hft, out=(hp, ht))
     barrier()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / reps
-    t_e = torch.tensor([e2e_ms], device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t_e.item())
+    e2e_ms = allmax(1e3 * (time.perf_counter() - t0) / reps)
     h2d = (hj.numel() + ha.numel() + ho.numel()) * 4 + 12
     d2h = (hp.numel() + ht.numel()) * 4
+    h2d_all, d2h_all = allmax(h2d) * world, allmax(d2h) * world     # bytes of the whole job per step (equal shards)
 
     if rank != 0:
         if dist is not None:
@@ -324,40 +441,56 @@ def main():
         return
 
     pk = peaks()
-    if args.gemm_mode == 2:
-        # dominant kernel = the persistent grouped GEMM; its launches of one frame run the whole LSTM stack of every stream once
+    seq_kernel = args.gemm_mode == 3 or (args.gemm_mode == 2 and B <= 128)
+    if args.gemm_mode >= 2:
+        # dominant kernel: the persistent tcgen05 kernel(s); their launches of one pass run the whole LSTM stack of every stream-frame once
         dom_flop = fpr.value * B * T * args.steps
-        pair = os.environ.get('RC_PH_PAIR', '0') not in ('', '0')
-        kname = (('rc_tc_phase_pair_kernel (persistent grouped tcgen05 GEMM on CTA pairs, cta_group::2 M=256' if pair else
-                  'rc_tc_phase_kernel (persistent grouped tcgen05 GEMM, one CTA per SM, 128 x 128 tiles from a global queue') +
-                 ': all linear1 / LSTM / linear2 layers of a phase of the frame in one launch, 3 launches per frame; kind::f16 on split-fp16 '
-                 'operands, 3 MMAs per fp32-accurate product; CUDA events around every launch)')
+        if seq_kernel:
+            kname = ('rc_seq_kernel<64> (persistent SEQUENCE kernel: frames 16..T-1 of the pass in ONE launch, one CTA per SM; 128 x 64 tcgen05 tiles of '
+                     'every linear1 / LSTM / linear2 layer and the per-frame row jobs in one dependency queue) + rc_tc_phase_kernel for the 16 warm-up '
+                     'frames; kind::f16 on split-fp16 operands, 3 MMAs per fp32-accurate product; CUDA events around every launch')
+        else:
+            kname = ('rc_tc_phase_kernel (persistent grouped tcgen05 GEMM, one CTA per SM, 128 x 128 tiles from a global queue: all linear1 / LSTM / '
+                     'linear2 layers of a phase of the frame in one launch, 3 launches per frame; kind::f16 on split-fp16 operands, 3 MMAs per '
+                     'fp32-accurate product; CUDA events around every launch)')
     else:
-        # dominant kernel: per timed step every (sequence, frame) row goes through 2 rnn4 LSTM-layer launches
         dom_flop = fpr.value * 2 * B * T * args.steps
         kname = ('rc_tc_kernel<128,3,LSTM> (rnn4 fused LSTM layer [rows,2560]x[2560,5120]; tcgen05 kind::f16 on split-fp16 operands, '
                  '3 MMAs per fp32-accurate product; CUDA events on its launch stream while the other lane runs concurrently)')
     dom_tflops = dom_flop / (tot_ms.value * 1e-3) / 1e12 if tot_ms.value > 0 else 0.0
+    per_gpu_ms = ms_step
     roofline = {'kernel': kname,
                 'bound': 'tensor',
                 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': dom_tflops / pk['tflops_sustained'], 'peak_source': 'bf16 sustained, of ' + pk['source'],
-                'traffic': dominant_traffic(args.gemm_mode), 'launches': int(nl.value), 'share_of_step': tot_ms.value / roof_ms_total,
-                'timed_with': 'a second pass of the same K steps with stream launches (%.1f ms per step) — the value pass replays a CUDA graph' % (roof_ms_total / args.steps),
+                'traffic': dominant_traffic(args.gemm_mode), 'launches': int(nl.value), 'share_of_step': tot_ms.value / (roof_ms * args.steps),
+                'timed_with': 'a second pass of the same K steps with stream launches (%.1f ms per step) — the value pass replays a CUDA graph' % roof_ms,
                 'tensor_pipe_frac': 3 * dom_tflops / pk['tflops_sustained'],   # 3 fp16 MMAs are issued per algorithmic fp32 product
-                'whole_path_tflops': FLOP_PER_FRAME * B * T / (ms_step * 1e-3) / 1e12,
-                'weight_stream_gbs': WEIGHT_BYTES * T / (ms_step * 1e-3) / 1e9}
+                'whole_path_tflops_per_gpu': FLOP_PER_FRAME * B * T / (per_gpu_ms * 1e-3) / 1e12,
+                'weight_stream_gbs_per_gpu': WEIGHT_BYTES * T / (per_gpu_ms * 1e-3) / 1e9,
+                'hbm_frac_weights': WEIGHT_BYTES * T / (per_gpu_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
+                'note': 'rank 0 of %d; per GPU a pass streams the 243 MB of weights once per frame: at %d sequences per GPU the frame is bound by %s'
+                        % (world, B, 'the tensor pipe' if B >= 512 else 'the depth of its dependency chain (12 dependent GEMM layers + row logic), not by HBM or the tensor pipe')}
+    cfg = workload_config(args, world, B)
+    run_info = dict({'sequences_per_gpu': B,
+                'l2': 'inputs (%.0f MB per GPU) + weights (243 MB) per step exceed the 126 MB L2' % ((hj.numel() + ha.numel() + ho.numel()) * 4 / 1e6),
+                'final_gather': 'one nccl gather of the flat [pose | tran] buffer to rank 0 inside the timed region' if world > 1 else 'none',
+                'launch': ('persistent sequence kernel after 16 warm-up frames (shards of <= 128 sequences)' if seq_kernel else
+                           'CUDA-graph replay of the per-frame launch sequence (Net.forward_offline default)')})
     line = {'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
-            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic',
-            'config': {'workload': 'offline_eval %d seq x %d frames per GPU (BASELINE configs[2])' % (B, T), 'conf': args.conf,
-                       'weights': 'random-init seed 0 (contact variant)', 'l2': 'inputs (%.0f MB) + weights (243 MB) per step exceed the 126 MB L2'
-                       % ((hj.numel() + ha.numel() + ho.numel()) * 4 / 1e6), 'final_gather': 'nccl gather to rank 0 inside the timed region' if world > 1 else 'none',
-                       'launch': 'CUDA-graph replay of the per-frame launch sequence (Net.forward_offline default)'},
+            'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': cfg, 'run': run_info,
             'clocks': clk, 'gpu_launches': int(launches),
-            'e2e': {'value': frames_step / (e2e_ms / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+            'e2e': {'value': frames_step / (e2e_ms / 1e3), 'unit': 'frames/s', 'h2d_bytes_per_step': int(h2d_all), 'd2h_bytes_per_step': int(d2h_all),
                     'ms_per_step': e2e_ms},
             'roofline': roofline}
+    if occ is not None:
+        occ['weight_stream_gbs_per_gpu'] = WEIGHT_BYTES * T / (occ['ms_per_step'] * 1e-3) / 1e9
+        occ['hbm_frac_weights'] = occ['weight_stream_gbs_per_gpu'] / pk['hbm_gbs']
+        occ['whole_path_tflops_per_gpu'] = FLOP_PER_FRAME * B * T / (occ['ms_per_step'] * 1e-3) / 1e12
+        occ['note'] = ('BASELINE configs[4]; every occluded frame runs the IMU-only branch AND the vision updater (rnn4 + rnn6 on re-projected key points, '
+                       'net/sig_mp.py:263-271), so all six LSTM stacks still run for every stream-frame; HBM figure = 243 MB of weights per frame per GPU over the measured copy peak')
+        line['occlusion'] = occ
 
     # ---- B=1 streaming latency (BASELINE configs[1]) ---------------------------------------------------------------
     if not args.no_stream_latency:
@@ -382,12 +515,23 @@ def main():
         line['streaming'] = {'batch': 1, 'latency_p50_us_forward_online': 1e6 * statistics.median(lat[20:]),
                              'device_us_per_frame_graph': dev_us, 'weight_stream_gbs': WEIGHT_BYTES / (dev_us * 1e-6) / 1e9,
                              'hbm_frac': WEIGHT_BYTES / (dev_us * 1e-6) / 1e9 / pk['hbm_gbs'], 'peak_source': 'hbm copy, of ' + pk['source']}
+    if not args.no_smplify:
+        try:
+            line['smplify'] = smplify_line(net, assets, dev, pk)
+        except Exception as e:                       # never lose the headline line to the secondary workload
+            line['smplify'] = {'error': '%s: %s' % (type(e).__name__, e)}
     if not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_reference_rate(sd, assets, args.cpu_frames, args.conf, 'aten')
+        line['cpu_baseline']['host_cpus'] = os.cpu_count()
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def smplify_line(net, assets, dev, pk):
+    """BASELINE configs[3]: fusion RNN -> SMPL FK -> SMPLify (max_iter = 5) on one 300-frame sequence, device-timed."""
+    raise RuntimeError('not wired yet')
 
 
 if __name__ == '__main__':
