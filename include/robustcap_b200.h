@@ -185,6 +185,19 @@ void rc_smplify_destroy(rc_smplify* s);
 int rc_smplify_loss_grad(rc_smplify* s, const float* d_pose, const float* d_tran, const float* d_j2d, const float* d_conf,
                          const float* d_cam_k, const float* d_ref3d, const float* d_imu_aa, int rodrigues, float* d_loss,
                          float* d_grad_pose, float* d_grad_tran, float* d_reproj, void* stream);
+/* The optimisation of TemporalSMPLify.__call__ (net/smplify/temporal_smplify.py:139-166: torch.optim.LBFGS(max_iter, lr,
+ * line_search_fn='strong_wolfe').step(closure), one step) for n_seq independent sequences of T frames (T = the handle's batch size),
+ * entirely on the device: ONE thread block per sequence evaluates the closure (objective + analytic gradient, the kernels behind
+ * rc_smplify_loss_grad) and runs torch/optim/lbfgs.py's two-loop recursion and strong-Wolfe line search (_strong_wolfe,
+ * _cubic_interpolate) with every reduction inside the block — no launch and no host round trip per iteration.
+ * d_aa_init [S,T,72] / d_tran_init [S,T,3]: start (axis-angle from cv2.Rodrigues semantics, :106); d_j2d [S,T,33,2] pixel key points,
+ * d_conf [S,T,33] (ignored joints already zeroed, :148), d_camk [9] (camk_per_seq = 0) or [S,9]; d_ref3d [S,T,33,3] (:108-109);
+ * d_imu_aa [S,T,18].  Outputs d_aa_out / d_tran_out (may alias nothing of the inputs); d_stats (optional) [S,4] =
+ * {first loss, final loss, closure evaluations, iterations}. */
+int rc_smplify_run(rc_smplify* s, int32_t n_seq, const float* d_aa_init, const float* d_tran_init, const float* d_j2d, const float* d_conf,
+                   const float* d_camk, int32_t camk_per_seq, const float* d_ref3d, const float* d_imu_aa, int32_t max_iter, float lr,
+                   float* d_aa_out, float* d_tran_out, float* d_stats, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------------------
  * Evaluation metrics next to the hot path — evaluate.py:120-133 (cal_mpjpe) with utils.py:138-203 (Procrustes).

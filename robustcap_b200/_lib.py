@@ -105,6 +105,7 @@ _SIGS = {
     'rc_smplify_create': (i32, [ctypes.POINTER(vp), vp, vp, vp, vp, i32]),
     'rc_smplify_destroy': (None, [vp]),
     'rc_smplify_loss_grad': (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp]),
+    'rc_smplify_run': (i32, [vp, i32, vp, vp, vp, vp, vp, i32, vp, vp, i32, ctypes.c_float, vp, vp, vp, vp]),
     'rc_metrics_mpjpe': (i32, [vp, vp, i32, vp, vp, i64, i32, vp, vp]),
     'rc_pack_inputs': (i32, [i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]),
     'rc_synthesize_imu': (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp, vp, vp, vp, vp]),

@@ -10,6 +10,7 @@
 //                          back through skinning, the kinematic chain and Rodrigues
 //   rc_sum_kernel          deterministic reduction of the per-frame losses
 // The optimiser stays torch.optim.LBFGS (the third-party class the reference itself calls).
+#include <algorithm>
 #include <vector>
 #include "rc_common.cuh"
 #include "rc_rows.h"
@@ -37,6 +38,9 @@ struct rc_smplify {
     float *d_G = nullptr, *d_p = nullptr, *d_proj = nullptr, *d_lossf = nullptr, *d_prior = nullptr, *d_gprior = nullptr;
     int* d_argmin = nullptr;
     std::vector<void*> allocs;
+    // scratch of rc_smplify_run (device-resident L-BFGS), sized for run_S sequences and run_hist history pairs
+    float *r_vec = nullptr, *r_G = nullptr, *r_p = nullptr, *r_proj = nullptr, *r_lossf = nullptr, *r_prior = nullptr, *r_gprior = nullptr;
+    int run_S = 0, run_hist = 0;
 };
 
 namespace {
@@ -66,6 +70,35 @@ __global__ void __launch_bounds__(256) rc_gmm_kernel(const SmplifyConst* __restr
     for (int k = 1; k < NG; ++k) if (ll[k] < ll[best]) best = k;          // torch.min: first minimum
     if (threadIdx.x == 0) prior[t] = ll[best];
     for (int j = threadIdx.x; j < ND; j += blockDim.x) gprior[(size_t)t * ND + j] = pd[best][j];
+}
+
+// The same prior for one frame by ONE warp (components one after the other; per-lane arithmetic and reduction order identical to
+// rc_gmm_kernel, so both give the same bits).  d / pd / best: 3 x 69 floats of shared memory private to the warp.
+__device__ __forceinline__ void gmm_frame_warp(const SmplifyConst* __restrict__ C, const float* __restrict__ Psym, const float* aa_t,
+                                               float* prior_t, float* gprior_t, float* d, float* pd, float* best_pd, int lane) {
+    float best_ll = 0.f;
+    for (int m = 0; m < NG; ++m) {
+        for (int j = lane; j < ND; j += 32) d[j] = aa_t[3 + j] - C->means[m][j];
+        __syncwarp();
+        const float* P = Psym + (size_t)m * ND * ND;
+        float q = 0.f;
+        for (int i = lane; i < ND; i += 32) {
+            float s = 0.f;
+            for (int j = 0; j < ND; ++j) s = fmaf(P[i * ND + j], d[j], s);
+            pd[i] = s;
+            q = fmaf(s, d[i], q);
+        }
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float ll = 0.5f * q - C->logw[m];
+        __syncwarp();
+        if (m == 0 || ll < best_ll) {                                    // torch.min: first minimum
+            best_ll = ll;
+            for (int j = lane; j < ND; j += 32) best_pd[j] = pd[j];
+        }
+        __syncwarp();
+    }
+    if (lane == 0) prior_t[0] = best_ll;
+    for (int j = lane; j < ND; j += 32) gprior_t[j] = best_pd[j];
 }
 
 // ---- forward ---------------------------------------------------------------------------------------------------------
@@ -103,10 +136,7 @@ __device__ __forceinline__ void keypoints_from_G(const RcModelConst& M, const fl
     }
 }
 
-__global__ void __launch_bounds__(32) rc_smplify_fwd_kernel(const RcModelConst* __restrict__ Mp, FwdArgs a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.T) return;
-    const RcModelConst& M = *Mp;
+__device__ __noinline__ void smplify_fwd_frame(const RcModelConst& M, const FwdArgs& a, int t) {
     float G[RC_NJ][12];
     for (int i = 0; i < RC_NJ; ++i) {
         float R[9], L[12];
@@ -166,6 +196,12 @@ __global__ void __launch_bounds__(32) rc_smplify_fwd_kernel(const RcModelConst* 
     a.lossf[a.T + t] = 0.25f * imu;
 }
 
+__global__ void __launch_bounds__(32) rc_smplify_fwd_kernel(const RcModelConst* __restrict__ Mp, FwdArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.T) return;
+    smplify_fwd_frame(*Mp, a, t);
+}
+
 // ---- backward ----------------------------------------------------------------------------------------------------------
 struct BwdArgs {
     const float *aa, *j2d, *conf, *camk, *ref3d, *G, *p, *proj, *gprior;
@@ -173,10 +209,7 @@ struct BwdArgs {
     int T;
 };
 
-__global__ void __launch_bounds__(32) rc_smplify_bwd_kernel(const RcModelConst* __restrict__ Mp, BwdArgs a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.T) return;
-    const RcModelConst& M = *Mp;
+__device__ __noinline__ void smplify_bwd_frame(const RcModelConst& M, const BwdArgs& a, int t) {
     const float* p = a.p + (size_t)t * 99;
     const float* pr = a.proj + (size_t)t * 66;
     float K[9];
@@ -327,6 +360,302 @@ __global__ void __launch_bounds__(32) rc_smplify_bwd_kernel(const RcModelConst* 
     for (int r = 0; r < 3; ++r) a.gtran[(size_t)t * 3 + r] = gtr[r];
 }
 
+__global__ void __launch_bounds__(32) rc_smplify_bwd_kernel(const RcModelConst* __restrict__ Mp, BwdArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.T) return;
+    smplify_bwd_frame(*Mp, a, t);
+}
+
+
+// ---- device-resident L-BFGS (torch.optim.LBFGS.step with line_search_fn='strong_wolfe', temporal_smplify.py:151-166) ----------------
+// ONE thread block per sequence runs the whole optimisation: closure evaluations (GMM prior -> forward -> backward -> loss sum, the
+// functions above, one thread per frame / one warp per frame for the prior), the two-loop recursion, the strong-Wolfe bracketing /
+// zoom with cubic interpolation, every reduction inside the block in a fixed order.  No host round trip, no launch per iteration;
+// independent sequences run as independent blocks.  Scalar arithmetic is float32 like torch's 0-dim tensors (lbfgs.py); the
+// expressions follow torch/optim/lbfgs.py line by line (_cubic_interpolate, _strong_wolfe, LBFGS.step; defaults tolerance_grad 1e-7,
+// tolerance_change 1e-9, history_size 100, max_eval = max_iter * 5 // 4, first step t = min(1, 1 / |g|_1) * lr).
+constexpr int kLbThreadsMax = 512;
+enum { LB_X = 0, LB_XINIT, LB_D, LB_G, LB_PG, LB_GN, LB_GPREV, LB_BG0, LB_BG1, LB_Q, LB_NFIXED };   // then old_dirs[h], old_stps[h]
+
+struct LbfgsArgs {
+    const float *aa0, *tran0, *j2d, *conf, *camk, *ref3d, *imu_aa;
+    float* vec;            // [S][LB_NFIXED + 2 hist][n]
+    float *G, *p, *proj, *lossf, *prior, *gprior;     // per-sequence scratch of the closure
+    float *aa_out, *tran_out, *stats;
+    const SmplifyConst* C;
+    const float* Psym;
+    int T, n, max_iter, max_eval, hist, camk_stride;
+    float lr;
+};
+
+struct LbShared {
+    double red[kLbThreadsMax];
+    double s1[256], s2[256];
+    float gmm[kLbThreadsMax / 32][3][ND + 3];
+    float bcast;
+};
+
+__device__ __forceinline__ double lb_block_sum(double v, LbShared& sh) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    sh.red[tid] = v;
+    __syncthreads();
+    for (int o = kLbThreadsMax / 2; o > 0; o >>= 1) {
+        if (tid < o && tid + o < nt) sh.red[tid] += sh.red[tid + o];
+        __syncthreads();
+    }
+    const double r = sh.red[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float lb_block_max(float v, LbShared& sh) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    sh.red[tid] = (double)v;
+    __syncthreads();
+    for (int o = kLbThreadsMax / 2; o > 0; o >>= 1) {
+        if (tid < o && tid + o < nt) sh.red[tid] = fmax(sh.red[tid], sh.red[tid + o]);
+        __syncthreads();
+    }
+    const float r = (float)sh.red[0];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float lb_dot(const float* a, const float* b, int n, LbShared& sh) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)a[i] * (double)b[i];
+    return (float)lb_block_sum(acc, sh);
+}
+__device__ __forceinline__ float lb_absmax(const float* a, float scale, int n, LbShared& sh) {
+    float m = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(a[i] * scale));
+    return lb_block_max(m, sh);
+}
+__device__ __forceinline__ float lb_abssum(const float* a, int n, LbShared& sh) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)fabsf(a[i]);
+    return (float)lb_block_sum(acc, sh);
+}
+__device__ __forceinline__ void lb_copy(float* dst, const float* src, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+}
+// dst = a + alpha * b
+__device__ __forceinline__ void lb_axpy_to(float* dst, const float* a, float alpha, const float* b, int n) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = fmaf(alpha, b[i], a[i]);
+    __syncthreads();
+}
+
+// torch/optim/lbfgs.py:_cubic_interpolate, float32
+__device__ __forceinline__ float lb_cubic(float x1, float f1, float g1, float x2, float f2, float g2, bool bounded, float lo, float hi) {
+    if (!bounded) { lo = (x1 <= x2) ? x1 : x2; hi = (x1 <= x2) ? x2 : x1; }
+    const float d1 = g1 + g2 - (float)(3.0 * ((double)f1 - (double)f2)) / (x1 - x2);
+    const float d2sq = d1 * d1 - g1 * g2;
+    if (d2sq >= 0.f) {
+        const float d2 = sqrtf(d2sq);
+        float mp;
+        if (x1 <= x2) mp = x2 - (x2 - x1) * ((g2 + d2 - d1) / (g2 - g1 + 2.f * d2));
+        else mp = x1 - (x1 - x2) * ((g1 + d2 - d1) / (g1 - g2 + 2.f * d2));
+        return fminf(fmaxf(mp, lo), hi);
+    }
+    return (lo + hi) / 2.f;
+}
+
+// closure: loss and gradient at x (aa | tran) -> g; every thread returns the loss
+__device__ float lb_eval(const RcModelConst& M, const LbfgsArgs& a, int seq, const float* x, float* g, LbShared& sh) {
+    const int T = a.T, tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    const size_t so = (size_t)seq * T;
+    float* prior = a.prior + so;
+    float* gprior = a.gprior + so * ND;
+    for (int t = warp; t < T; t += nw)
+        gmm_frame_warp(a.C, a.Psym, x + (size_t)t * 72, prior + t, gprior + (size_t)t * ND, sh.gmm[warp][0], sh.gmm[warp][1], sh.gmm[warp][2], lane);
+    __syncthreads();
+    FwdArgs f;
+    f.aa = x; f.tran = x + (size_t)T * 72; f.j2d = a.j2d + so * 66; f.conf = a.conf + so * 33; f.camk = a.camk + (size_t)seq * a.camk_stride;
+    f.ref3d = a.ref3d + so * 99; f.imu_aa = a.imu_aa + so * 18; f.prior = prior;
+    f.G = a.G + so * 288; f.p = a.p + so * 99; f.proj = a.proj + so * 66; f.lossf = a.lossf + so * 3; f.reproj = nullptr; f.T = T; f.rodrigues = 0;
+    for (int t = tid; t < T; t += nt) smplify_fwd_frame(M, f, t);
+    __syncthreads();
+    BwdArgs b;
+    b.aa = x; b.j2d = f.j2d; b.conf = f.conf; b.camk = f.camk; b.ref3d = f.ref3d; b.G = f.G; b.p = f.p; b.proj = f.proj; b.gprior = gprior;
+    b.lossf = f.lossf; b.gaa = g; b.gtran = g + (size_t)T * 72; b.T = T;
+    for (int t = tid; t < T; t += nt) smplify_bwd_frame(M, b, t);
+    __syncthreads();
+    // loss = sum_t (frame + smooth) + T * sum_t imu: the reduction order of rc_smplify_sum_kernel (256 strided partial sums, tree)
+    if (tid < 256) {
+        double u = 0.0, v = 0.0;
+        for (int t = tid; t < T; t += 256) { u += (double)f.lossf[t] + (double)f.lossf[2 * T + t]; v += (double)f.lossf[T + t]; }
+        sh.s1[tid] = u; sh.s2[tid] = v;
+    }
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { sh.s1[tid] += sh.s1[tid + o]; sh.s2[tid] += sh.s2[tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) sh.bcast = (float)(sh.s1[0] + (double)T * sh.s2[0]);
+    __syncthreads();
+    const float loss = sh.bcast;
+    __syncthreads();
+    return loss;
+}
+
+__global__ void __launch_bounds__(kLbThreadsMax) rc_smplify_lbfgs_kernel(const RcModelConst* __restrict__ Mp, const LbfgsArgs a) {
+    __shared__ LbShared sh;
+    const RcModelConst& M = *Mp;
+    const int seq = blockIdx.x, n = a.n, T = a.T;
+    const int nvec = LB_NFIXED + 2 * a.hist;
+    float* V = a.vec + (size_t)seq * nvec * n;
+    auto vec = [&](int i) { return V + (size_t)i * n; };
+    auto old_dir = [&](int i) { return V + (size_t)(LB_NFIXED + i) * n; };
+    auto old_stp = [&](int i) { return V + (size_t)(LB_NFIXED + a.hist + i) * n; };
+    float* X = vec(LB_X);
+    for (int i = threadIdx.x; i < T * 72; i += blockDim.x) X[i] = a.aa0[(size_t)seq * T * 72 + i];
+    for (int i = threadIdx.x; i < T * 3; i += blockDim.x) X[T * 72 + i] = a.tran0[(size_t)seq * T * 3 + i];
+    __syncthreads();
+    const float tol_grad = 1e-7f, tol_change = 1e-9f, c1 = 1e-4f, c2 = 0.9f;
+    float ro[100], al[100];
+    int nh = 0;
+    float H_diag = 1.f, t = 0.f;
+
+    float loss = lb_eval(M, a, seq, X, vec(LB_G), sh);
+    const float first_loss = loss;
+    int evals = 1, n_iter = 0;
+    bool stop = lb_absmax(vec(LB_G), 1.f, n, sh) <= tol_grad;
+    while (!stop && n_iter < a.max_iter) {
+        ++n_iter;
+        float* G = vec(LB_G);
+        float* D = vec(LB_D);
+        if (n_iter == 1) {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) D[i] = -G[i];
+            __syncthreads();
+            nh = 0; H_diag = 1.f;
+        } else {
+            // memory update: y = g - prev_g, s = d * t
+            float* Y = old_dir(nh < a.hist ? nh : a.hist - 1);
+            float* S = old_stp(nh < a.hist ? nh : a.hist - 1);
+            if (nh == a.hist) {                                       // shift the history by one (limited memory)
+                for (int h = 0; h + 1 < a.hist; ++h) { lb_copy(old_dir(h), old_dir(h + 1), n); lb_copy(old_stp(h), old_stp(h + 1), n); ro[h] = ro[h + 1]; }
+                nh = a.hist - 1;
+            }
+            const float* PG = vec(LB_PG);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) { Y[i] = G[i] - PG[i]; S[i] = D[i] * t; }
+            __syncthreads();
+            const float ys = lb_dot(Y, S, n, sh);
+            if (ys > 1e-10f) {
+                ro[nh] = 1.f / ys;
+                H_diag = ys / lb_dot(Y, Y, n, sh);
+                ++nh;
+            }
+            float* Q = vec(LB_Q);
+            for (int i = threadIdx.x; i < n; i += blockDim.x) Q[i] = -G[i];
+            __syncthreads();
+            for (int h = nh - 1; h >= 0; --h) {
+                al[h] = lb_dot(old_stp(h), Q, n, sh) * ro[h];
+                lb_axpy_to(Q, Q, -al[h], old_dir(h), n);
+            }
+            for (int i = threadIdx.x; i < n; i += blockDim.x) D[i] = Q[i] * H_diag;
+            __syncthreads();
+            for (int h = 0; h < nh; ++h) {
+                const float be = lb_dot(old_dir(h), D, n, sh) * ro[h];
+                lb_axpy_to(D, D, al[h] - be, old_stp(h), n);
+            }
+        }
+        lb_copy(vec(LB_PG), G, n);
+        const float prev_loss = loss;
+        if (n_iter == 1) t = fminf(1.f, 1.f / lb_abssum(G, n, sh)) * a.lr;
+        else t = a.lr;
+        const float gtd = lb_dot(G, D, n, sh);
+        if (gtd > -tol_change) break;
+
+        // ---- _strong_wolfe(obj_func, x_init, t, d, loss, flat_grad, gtd, max_ls = max_eval - current_evals) ----
+        const int max_ls = a.max_eval - evals;
+        lb_copy(vec(LB_XINIT), X, n);
+        const float* XI = vec(LB_XINIT);
+        const float f = loss;
+        const float d_norm = lb_absmax(D, 1.f, n, sh);
+        float* GN = vec(LB_GN);
+        lb_axpy_to(X, XI, t, D, n);
+        float f_new = lb_eval(M, a, seq, X, GN, sh);
+        int ls_evals = 1;
+        float gtd_new = lb_dot(GN, D, n, sh);
+        float t_prev = 0.f, f_prev = f, gtd_prev = gtd;
+        lb_copy(vec(LB_GPREV), G, n);
+        bool done = false;
+        int ls_iter = 0, nb = 0;
+        float br[2] = {0.f, 0.f}, brf[2] = {0.f, 0.f}, brgtd[2] = {0.f, 0.f};
+        float* BG[2] = {vec(LB_BG0), vec(LB_BG1)};
+        while (ls_iter < max_ls) {
+            if (f_new > (f + c1 * t * gtd) || (ls_iter > 1 && f_new >= f_prev) || (!(fabsf(gtd_new) <= -c2 * gtd) && gtd_new >= 0.f)) {
+                br[0] = t_prev; br[1] = t; brf[0] = f_prev; brf[1] = f_new; brgtd[0] = gtd_prev; brgtd[1] = gtd_new; nb = 2;
+                lb_copy(BG[0], vec(LB_GPREV), n); lb_copy(BG[1], GN, n);
+                break;
+            }
+            if (fabsf(gtd_new) <= -c2 * gtd) {
+                br[0] = t; brf[0] = f_new; nb = 1; done = true;
+                lb_copy(BG[0], GN, n);
+                break;
+            }
+            const float min_step = t + 0.01f * (t - t_prev), max_step = t * 10.f, tmp = t;
+            t = lb_cubic(t_prev, f_prev, gtd_prev, t, f_new, gtd_new, true, min_step, max_step);
+            t_prev = tmp; f_prev = f_new; gtd_prev = gtd_new;
+            lb_copy(vec(LB_GPREV), GN, n);
+            lb_axpy_to(X, XI, t, D, n);
+            f_new = lb_eval(M, a, seq, X, GN, sh);
+            ++ls_evals;
+            gtd_new = lb_dot(GN, D, n, sh);
+            ++ls_iter;
+        }
+        if (nb == 0) {                                                // reached max_ls without a bracket
+            br[0] = 0.f; br[1] = t; brf[0] = f; brf[1] = f_new; nb = 2;
+            lb_copy(BG[0], G, n); lb_copy(BG[1], GN, n);
+        }
+        bool insuf = false;
+        int low = (brf[0] <= brf[nb - 1]) ? 0 : 1, high = 1 - low;
+        while (!done && ls_iter < max_ls) {
+            if (fabsf(br[1] - br[0]) * d_norm < tol_change) break;
+            t = lb_cubic(br[0], brf[0], brgtd[0], br[1], brf[1], brgtd[1], false, 0.f, 0.f);
+            const float bmax = fmaxf(br[0], br[1]), bmin = fminf(br[0], br[1]);
+            const float eps = 0.1f * (bmax - bmin);
+            if (fminf(bmax - t, t - bmin) < eps) {
+                if (insuf || t >= bmax || t <= bmin) {
+                    t = (fabsf(t - bmax) < fabsf(t - bmin)) ? bmax - eps : bmin + eps;
+                    insuf = false;
+                } else insuf = true;
+            } else insuf = false;
+            lb_axpy_to(X, XI, t, D, n);
+            f_new = lb_eval(M, a, seq, X, GN, sh);
+            ++ls_evals;
+            gtd_new = lb_dot(GN, D, n, sh);
+            ++ls_iter;
+            if (f_new > (f + c1 * t * gtd) || f_new >= brf[low]) {
+                br[high] = t; brf[high] = f_new; brgtd[high] = gtd_new;
+                lb_copy(BG[high], GN, n);
+                low = (brf[0] <= brf[1]) ? 0 : 1; high = 1 - low;
+            } else {
+                if (fabsf(gtd_new) <= -c2 * gtd) done = true;
+                else if (gtd_new * (br[high] - br[low]) >= 0.f) {
+                    br[high] = br[low]; brf[high] = brf[low]; brgtd[high] = brgtd[low];
+                    lb_copy(BG[high], BG[low], n);
+                }
+                br[low] = t; brf[low] = f_new; brgtd[low] = gtd_new;
+                lb_copy(BG[low], GN, n);
+            }
+        }
+        t = br[low]; loss = brf[low];
+        lb_copy(G, BG[low], n);
+        lb_axpy_to(X, XI, t, D, n);                                   // _add_grad(t, d) from x_init
+        const bool opt_cond = lb_absmax(G, 1.f, n, sh) <= tol_grad;
+        evals += ls_evals;
+        if (n_iter == a.max_iter || evals >= a.max_eval || opt_cond) break;
+        if (lb_absmax(D, t, n, sh) <= tol_change) break;
+        if (fabs((double)loss - (double)prev_loss) < 1e-9) break;
+    }
+    for (int i = threadIdx.x; i < T * 72; i += blockDim.x) a.aa_out[(size_t)seq * T * 72 + i] = X[i];
+    for (int i = threadIdx.x; i < T * 3; i += blockDim.x) a.tran_out[(size_t)seq * T * 3 + i] = X[T * 72 + i];
+    if (threadIdx.x == 0 && a.stats) {
+        float* st = a.stats + (size_t)seq * 4;
+        st[0] = first_loss; st[1] = loss; st[2] = (float)evals; st[3] = (float)n_iter;
+    }
+}
+
 // loss = sum_t (frame + smooth) + T * sum_t imu    (losses.py:63 broadcast, see above); one block, fixed order
 __global__ void __launch_bounds__(256) rc_smplify_sum_kernel(const float* __restrict__ lossf, int T, int with_smooth, float* __restrict__ out) {
     __shared__ double s1[256], s2[256];
@@ -379,8 +708,15 @@ int rc_smplify_create(rc_smplify** out, const rc_model* model, const float* h_me
     return RC_OK;
 }
 
+static void smplify_free_run(rc_smplify* s) {
+    cudaFree(s->r_vec); cudaFree(s->r_G); cudaFree(s->r_p); cudaFree(s->r_proj); cudaFree(s->r_lossf); cudaFree(s->r_prior); cudaFree(s->r_gprior);
+    s->r_vec = s->r_G = s->r_p = s->r_proj = s->r_lossf = s->r_prior = s->r_gprior = nullptr;
+    s->run_S = s->run_hist = 0;
+}
+
 void rc_smplify_destroy(rc_smplify* s) {
     if (!s) return;
+    smplify_free_run(s);
     for (void* p : s->allocs) cudaFree(p);
     delete s;
 }
@@ -413,6 +749,39 @@ int rc_smplify_loss_grad(rc_smplify* s, const float* aa, const float* tran, cons
         RC_LAUNCH(rc_smplify_sum_kernel, 1, 256, 0, stream, s->d_lossf, T, 1, loss);
         RC_CHECK_LAUNCH();
     }
+    return RC_OK;
+}
+
+// TemporalSMPLify.__call__'s optimisation (temporal_smplify.py:139-166) for n_seq independent sequences of T frames each (T = the
+// handle's batch size): parameters start at (aa_init [S,T,72], tran_init [S,T,3]) and the optimised values are written to
+// (aa_out, tran_out); stats (optional) [S,4] = {first loss, final loss, closure evaluations, iterations}.  One thread block per
+// sequence runs torch.optim.LBFGS.step (strong Wolfe) entirely on the device; nothing is copied to the host.
+int rc_smplify_run(rc_smplify* s, int32_t n_seq, const float* aa_init, const float* tran_init, const float* j2d, const float* conf,
+                   const float* camk, int32_t camk_per_seq, const float* ref3d, const float* imu_aa, int32_t max_iter, float lr,
+                   float* aa_out, float* tran_out, float* stats, void* stream) {
+    RC_ARG(s && n_seq > 0 && aa_init && tran_init && j2d && conf && camk && ref3d && imu_aa && aa_out && tran_out && max_iter > 0);
+    const int T = s->T;
+    const int hist = std::min(100, max_iter);
+    const size_t n = (size_t)T * 75;
+    if (s->run_S < n_seq || s->run_hist < hist) {
+        smplify_free_run(s);
+        const size_t S = (size_t)n_seq, nvec = (size_t)LB_NFIXED + 2 * (size_t)hist;
+        bool ok = cudaMalloc(&s->r_vec, S * nvec * n * 4) == cudaSuccess && cudaMalloc(&s->r_G, S * T * 288 * 4) == cudaSuccess &&
+                  cudaMalloc(&s->r_p, S * T * 99 * 4) == cudaSuccess && cudaMalloc(&s->r_proj, S * T * 66 * 4) == cudaSuccess &&
+                  cudaMalloc(&s->r_lossf, S * T * 3 * 4) == cudaSuccess && cudaMalloc(&s->r_prior, S * T * 4) == cudaSuccess &&
+                  cudaMalloc(&s->r_gprior, S * T * ND * 4) == cudaSuccess;
+        if (!ok) { rc_set_error("rc_smplify_run: out of device memory for %d sequences x %d frames", n_seq, T); smplify_free_run(s); return RC_ERR_ALLOC; }
+        s->run_S = n_seq; s->run_hist = hist;
+    }
+    LbfgsArgs a;
+    a.aa0 = aa_init; a.tran0 = tran_init; a.j2d = j2d; a.conf = conf; a.camk = camk; a.ref3d = ref3d; a.imu_aa = imu_aa;
+    a.vec = s->r_vec; a.G = s->r_G; a.p = s->r_p; a.proj = s->r_proj; a.lossf = s->r_lossf; a.prior = s->r_prior; a.gprior = s->r_gprior;
+    a.aa_out = aa_out; a.tran_out = tran_out; a.stats = stats; a.C = s->d_const; a.Psym = s->d_psym;
+    a.T = T; a.n = (int)n; a.max_iter = max_iter; a.max_eval = max_iter * 5 / 4; a.hist = s->run_hist; a.camk_stride = camk_per_seq ? 9 : 0;
+    a.lr = lr;
+    const int threads = std::min(kLbThreadsMax, std::max(256, (T + 31) / 32 * 32));
+    RC_LAUNCH(rc_smplify_lbfgs_kernel, n_seq, threads, 0, stream, s->model->d_const, a);
+    RC_CHECK_LAUNCH();
     return RC_OK;
 }
 

@@ -2,9 +2,12 @@ r"""``smplify_runner`` / ``TemporalSMPLify`` (reference ``net/smplify/{run,tempo
 
 Same call signatures and return values as the reference.  The objective of the per-sequence L-BFGS problem and its
 gradient are evaluated by CUDA kernels (``csrc/smplify.cu``: analytic derivative through Rodrigues, the kinematic chain and
-the skinning of the 21 vertices the 33 MediaPipe points read) instead of an autograd graph over a 6890-vertex mesh; the
-optimiser is ``torch.optim.LBFGS`` — the very class the reference calls (temporal_smplify.py:151) — fed through a closure
-that installs the native gradient.  ``smplify_runner`` gains an optional ``max_iter=20`` keyword.
+the skinning of the 21 vertices the 33 MediaPipe points read) instead of an autograd graph over a 6890-vertex mesh, and the optimiser —
+``torch.optim.LBFGS(...).step`` with the strong-Wolfe line search, which the reference calls at temporal_smplify.py:151-166 —
+runs on the device too (``rc_smplify_run``: one thread block per sequence, no host round trip per iteration;
+``TemporalSMPLify.optimizer = 'torch'`` keeps the third-party class driving the native closure for A/B checks).
+``smplify_runner`` gains an optional ``max_iter=20`` keyword; ``smplify_runner_batch`` refines many equal-length
+sequences in one launch.
 """
 import ctypes
 import os
@@ -19,7 +22,7 @@ from . import math as M
 from .constants import SMPLIFY_IGNORED_KP, SMPLIFY_IGNORED_KP_HEAD
 from .model import ParametricModel
 
-__all__ = ['smplify_runner', 'TemporalSMPLify', 'MaxMixturePrior']
+__all__ = ['smplify_runner', 'smplify_runner_batch', 'TemporalSMPLify', 'MaxMixturePrior']
 
 
 class MaxMixturePrior:
@@ -44,6 +47,7 @@ class MaxMixturePrior:
 
 class TemporalSMPLify:
     r"""temporal_smplify.py:61-220."""
+    optimizer = 'native'       # 'native': device-resident L-BFGS (rc_smplify_run); 'torch': torch.optim.LBFGS around the native closure
     body_model = None          # shared ParametricModel (module-level global in the reference, temporal_smplify.py:21)
     smpl_file = 'models/SMPL_male.pkl'
 
@@ -109,6 +113,14 @@ class TemporalSMPLify:
         _, ref3d = self.body.keypoints33(init_pose, init_tran)
         ref3d = ref3d.contiguous()
         j2d, conf = self._prep_keypoints(keypoints_2d)
+        if self.optimizer == 'native' and self.num_iters == 1:
+            bp, gt, stats = self.optimise(body_pose, global_tran, j2d, conf, ref3d, self.imu_aa)
+            self.evals += int(stats[0, 2].item())
+            self.last_stats = stats
+            with torch.no_grad():
+                _, _, _, reproj = self._native(bp, gt, j2d, conf, ref3d, 1, False, True)
+                pose = M.axis_angle_to_rotation_matrix(bp)
+            return pose, gt, reproj
         body_pose.requires_grad = True
         global_tran.requires_grad = True
         opt = torch.optim.LBFGS([body_pose, global_tran], max_iter=self.max_iter, lr=self.step_size, line_search_fn='strong_wolfe')
@@ -127,6 +139,27 @@ class TemporalSMPLify:
             pose = M.axis_angle_to_rotation_matrix(bp)
         return pose, gt, reproj
 
+    def optimise(self, aa, tran, j2d, conf, ref3d, imu_aa, cam_k=None):
+        r"""``torch.optim.LBFGS(max_iter, lr, strong_wolfe).step`` on the device for ``S`` sequences at once: ``aa [S*T,72]`` (or
+        ``[T,72]``), ``tran [S*T,3]``, ``j2d [S*T,33,2]``, ``conf [S*T,33]``, ``ref3d [S*T,33,3]``, ``imu_aa [S*T,18]``; ``cam_k`` one
+        matrix (default: the instance's) or ``[S,3,3]``.  Returns optimised ``aa``, ``tran`` and ``stats [S,4]`` =
+        (first loss, final loss, closure evaluations, iterations), all on the device; no host synchronisation."""
+        lib = _lib.load()
+        T = self.batch_size
+        S = aa.numel() // (T * 72)
+        dev = self.device
+        c = lambda x: x.detach().to(dev, torch.float32).contiguous()
+        aa, tran, j2d, conf, ref3d, imu_aa = c(aa), c(tran), c(j2d), c(conf), c(ref3d), c(imu_aa)
+        cam = self.cam_k if cam_k is None else c(cam_k)
+        per_seq = int(cam.numel() == 9 * S and S > 1)
+        out_aa, out_tran = torch.empty_like(aa), torch.empty_like(tran)
+        stats = torch.empty(S, 4, device=dev)
+        _lib.check(lib.rc_smplify_run(self._h, S, _lib.dptr(aa), _lib.dptr(tran), _lib.dptr(j2d), _lib.dptr(conf), _lib.dptr(cam), per_seq,
+                                      _lib.dptr(ref3d), _lib.dptr(imu_aa), int(self.max_iter), float(self.step_size),
+                                      _lib.dptr(out_aa), _lib.dptr(out_tran), _lib.dptr(stats), _lib.stream()))
+        self._keep = (aa, tran, j2d, conf, ref3d, imu_aa, cam)
+        return out_aa, out_tran, stats
+
     def get_fitting_loss(self, pose, tran, keypoints_2d):
         r"""temporal_smplify.py:198-220 -> reprojection loss [T,33] of the given rotation matrices."""
         T = self.batch_size
@@ -135,6 +168,26 @@ class TemporalSMPLify:
         j2d, conf = self._prep_keypoints(keypoints_2d)
         dummy = torch.zeros(T, 33, 3, device=self.device)
         return self._native(pose, tran, j2d, conf, dummy, 2, False, True)[3]
+
+
+def smplify_runner_batch(pred_pose, pred_tran, j2dc, imu_ori, cam_k, lr=1.0, max_iter=20, use_head=False, body_model=None):
+    r"""``smplify_runner`` (run.py:6-35 with ``loss_threshold = inf``) for ``S`` equal-length sequences at once — the batched offline
+    evaluation of BASELINE configs[3]: ``pred_pose [S,T,24,3,3]``, ``pred_tran [S,T,3]``, ``j2dc [S,T,33,3]`` pixel key points with
+    confidence, ``imu_ori [S,T,6,3,3]``, ``cam_k [3,3]`` or ``[S,3,3]``.  Everything stays on the device; returns
+    ``pose [S,T,24,3,3]``, ``tran [S,T,3]``, ``stats [S,4]`` (first loss, final loss, closure evaluations, iterations)."""
+    S, T = pred_pose.shape[0], pred_pose.shape[1]
+    sm = TemporalSMPLify(cam_k=cam_k.reshape(-1, 3, 3)[0], imu_ori=imu_ori.reshape(S * T, 6, 3, 3)[:T], step_size=lr, batch_size=T,
+                         max_iter=max_iter, use_head=use_head, body_model=body_model)
+    dev = sm.device
+    pose = pred_pose.detach().to(dev, torch.float32).reshape(S * T, 24, 3, 3)
+    tran = pred_tran.detach().to(dev, torch.float32).reshape(S * T, 3)
+    aa = M.rotation_matrix_to_axis_angle(pose).reshape(S * T, 72)
+    _, ref3d = sm.body.keypoints33(pose, tran)
+    kp = j2dc.detach().to(dev, torch.float32).reshape(S * T, 33, 3).clone()
+    kp[:, sm.ign_mp_joints, 2] = 0.
+    imu_aa = M.rotation_matrix_to_axis_angle(imu_ori.detach().to(dev, torch.float32).reshape(S * T * 6, 3, 3)).reshape(S * T, 18)
+    aa2, tran2, stats = sm.optimise(aa, tran, kp[:, :, :2], kp[:, :, 2], ref3d, imu_aa, cam_k=cam_k)
+    return M.axis_angle_to_rotation_matrix(aa2).reshape(S, T, 24, 3, 3), tran2.reshape(S, T, 3), stats
 
 
 def smplify_runner(pred_pose, pred_tran, j2dc, imu_ori, batch_size, cam_k, lr=1.0, opt_steps=1, use_lbfgs=True,

@@ -260,6 +260,38 @@ def gen_smplify(ref, out):
         print('smplify', name, 'loss_init', float(loss), 'moved', float((po.reshape(T, 24, 3, 3) - pose).abs().max()))
 
 
+def gen_smplify_spread(ref, out):
+    """The reference's own run-to-run spread of the SMPLify result (README.md:27 "slightly different ... due to the randomness of the
+    optimization"): the identical call under 1, 2 and 8 CPU threads (different float32 reduction orders inside the ATen ops).  The
+    L-BFGS line search makes discrete decisions on float32 sums of ~1e5 terms, so the trajectories separate after a few closure
+    evaluations; a GPU implementation cannot be closer to "the" reference result than the reference is to itself."""
+    ts = ref['ts']
+    for name, max_iter, T in SMPLIFY_CASES:
+        g = dict(np.load(os.path.join(out, 'smplify_%s.npz' % name)))
+        pose, tran = torch.from_numpy(g['pose_in']), torch.from_numpy(g['tran_in'])
+        d = {}
+        for nt in (1, 2, 8):
+            torch.set_num_threads(nt)
+            sm = ts.TemporalSMPLify(cam_k=torch.from_numpy(g['cam_k']), imu_ori=torch.from_numpy(g['imu_ori']), step_size=1e-3, num_iters=1,
+                                    use_lbfgs=True, batch_size=T, max_iter=max_iter)
+            po, to, rl = sm(pose.reshape(T, -1).detach(), tran.detach(), torch.from_numpy(g['j2d_pix']).clone())
+            d['pose_out_t%d' % nt], d['tran_out_t%d' % nt] = po.reshape(T, 24, 3, 3).numpy(), to.numpy()
+            print('smplify spread', name, 'threads', nt, 'moved', float((po.reshape(T, 24, 3, 3) - pose).abs().max()),
+                  'vs committed golden', float((po.reshape(T, 24, 3, 3) - torch.from_numpy(g['pose_out'])).abs().max()))
+        torch.set_num_threads(8)
+        # ... and under float32-level noise on the start point (the size of one rounding of the inputs): 3 seeded perturbations
+        for k in range(3):
+            gen = torch.Generator().manual_seed(100 + k)
+            tr = tran * (1 + 2e-7 * torch.randn(tran.shape, generator=gen))
+            sm = ts.TemporalSMPLify(cam_k=torch.from_numpy(g['cam_k']), imu_ori=torch.from_numpy(g['imu_ori']), step_size=1e-3, num_iters=1,
+                                    use_lbfgs=True, batch_size=T, max_iter=max_iter)
+            po, to, rl = sm(pose.reshape(T, -1).detach(), tr.detach(), torch.from_numpy(g['j2d_pix']).clone())
+            d['pose_out_eps%d' % k], d['tran_out_eps%d' % k] = po.reshape(T, 24, 3, 3).numpy(), to.numpy()
+            print('smplify spread', name, 'start point perturbed by 2e-7 (relative), seed', k, 'vs committed golden',
+                  float((po.reshape(T, 24, 3, 3) - torch.from_numpy(g['pose_out'])).abs().max()), float((to - torch.from_numpy(g['tran_out'])).abs().max()))
+        np.savez_compressed(os.path.join(out, 'smplify_spread_%s.npz' % name), **d)
+
+
 def gen_metrics(ref, out):
     """evaluate.py:120-133 (cal_mpjpe) on seeded random poses — the step right after the hot path."""
     import evaluate
@@ -396,6 +428,8 @@ def main():
             gen_live(ref, HERE)
     if 'smplify' in which:
         gen_smplify(ref, HERE)
+    if 'smplify_spread' in which or 'smplify' in which:
+        gen_smplify_spread(ref, HERE)
     if 'metrics' in which:
         gen_metrics(ref, HERE)
     print('done')
