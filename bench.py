@@ -512,8 +512,10 @@ def main():
         g1.record()
         torch.cuda.synchronize()
         dev_us = 1e3 * g0.elapsed_time(g1) / 300
-        line['streaming'] = {'batch': 1, 'latency_p50_us_forward_online': 1e6 * statistics.median(lat[20:]),
-                             'device_us_per_frame_graph': dev_us, 'weight_stream_gbs': WEIGHT_BYTES / (dev_us * 1e-6) / 1e9,
+        line['streaming'] = {'batch': 1, 'kernel': 'rc_stream2_kernel: one launch per frame, one CTA per SM, weights staged through a shared-memory ring by '
+                                                   'cp.async.bulk (TMA), recurrent halves W_hh.h off the dependency chain, 8 split-phase grid barriers',
+                             'latency_p50_us_forward_online': 1e6 * statistics.median(lat[20:]),
+                             'device_us_per_frame': dev_us, 'weight_stream_gbs': WEIGHT_BYTES / (dev_us * 1e-6) / 1e9,
                              'hbm_frac': WEIGHT_BYTES / (dev_us * 1e-6) / 1e9 / pk['hbm_gbs'], 'peak_source': 'hbm copy, of ' + pk['source']}
     if not args.no_smplify:
         try:

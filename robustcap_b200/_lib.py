@@ -12,7 +12,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 SO_PATH = os.path.join(CSRC, 'librobustcap_b200.so')
-SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'phase_tc.cu', 'seq_tc.cu', 'stream.cu', 'metrics.cu', 'pipeline.cu']
+SOURCES = ['rotations.cu', 'kinematics.cu', 'fusion.cu', 'smplify.cu', 'gemm_tc.cu', 'phase_tc.cu', 'seq_tc.cu', 'stream.cu', 'stream2.cu', 'metrics.cu', 'pipeline.cu']
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']
 

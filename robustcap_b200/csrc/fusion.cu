@@ -880,7 +880,7 @@ void rc_state_destroy(rc_state* s) {
     if (!s) return;
     if (s->graph) cudaGraphExecDestroy(s->graph);
     if (s->on_graph) cudaGraphExecDestroy(s->on_graph);
-    cudaFree(s->sk_bar); cudaFree(s->sk_rows);
+    cudaFree(s->sk_bar); cudaFree(s->sk_rows); cudaFree(s->s2_bar); cudaFree(s->s2_ts);
     cudaFree(s->on_din); cudaFree(s->on_dout); cudaFreeHost(s->on_hin); cudaFreeHost(s->on_hout);
     rc_seq_destroy(s);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
@@ -971,6 +971,8 @@ int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const f
     io.pose = s->on_dout; io.tran = s->on_dout + 216; io.sp = 216; io.st = 3; io.d_t = nullptr; io.first_mode = 1;
     if (rc_stream_supported(s)) {
         RC_TRY(rc_stream_frame(s, io, first_frame, stream));    // the whole frame as one cooperative kernel (stream.cu)
+    } else if (!first_frame && rc_stream2_supported(s)) {
+        RC_TRY(rc_stream2_frame(s, io, 0, stream));             // one cooperative kernel, weights TMA-staged through shared memory (stream2.cu)
     } else if (first_frame) {
         RC_TRY(enqueue_step(s, io, 1, false, stream));          // extra rnn6 pass (sig_mp.py:155-156): direct launches
     } else {
@@ -1021,6 +1023,11 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
     // side stream even when the list is empty, longer than prep + lists, so nothing was gained: 525 vs 527 us per frame.)
     RC_TRY(enqueue_step(s, io, any_first_frame, true, stream));
     if (T == 1) return RC_OK;
+    if (s->B == 1 && !lengths && rc_stream2_supported(s) && !rc_stream_supported(s)) {
+        // a single stream: one TMA-staged cooperative kernel per frame (stream2.cu)
+        for (int t = 1; t < T; ++t) RC_TRY(rc_stream2_frame(s, io, t, stream));
+        return RC_OK;
+    }
     // Sequence kernel: forced by gemm mode 3; chosen automatically in the default mode 2 for small shards (<= 128 streams = one
     // row block, e.g. the 8-GPU split of 1024 sequences), where a frame is bound by its dependency chain and the 13 launch
     // boundaries of the multi-launch path cost more than the masked (uncompacted) passes of the sequence kernel.

@@ -53,6 +53,10 @@ struct rc_net {
     bool tc_ready = false;
     // sequence kernel (seq_tc.cu): in mode 2 it is chosen automatically for batches of at most seq_auto_B streams; the first
     // seq_warm frames of a sequence (where most streams re-seed rnn2 through init_net) always go through the multi-launch path
+    // single-stream TMA-staged kernel (stream2.cu): LSTM weights split into contiguous input / recurrent halves [4H, H]
+    bool s2_ready = false;
+    float* s2_Wx[NNETS][2] = {};
+    float* s2_Wh[NNETS][2] = {};
     int seq_auto_B = 128;
     int seq_warm = 16;
     int cfg_version = 0;        // bumped by rc_net_set_config: captured CUDA graphs bake the config into kernel arguments
@@ -115,6 +119,10 @@ struct rc_state {
     void* on_graph_stream = nullptr;
     long long on_graph_nodes = 0;
     int on_graph_cfg_version = -1;
+    // single-stream TMA-staged cooperative kernel (stream2.cu)
+    unsigned* s2_bar = nullptr;
+    int s2_grid = 0, s2_parity = 0;
+    unsigned long long* s2_ts = nullptr;
     // single-stream cooperative kernel (stream.cu)
     unsigned* sk_bar = nullptr;
     int* sk_rows = nullptr;            // [0] = row 0, [1] = count 1, [4..5] = frame flags / need_init
@@ -144,3 +152,6 @@ struct StepIO {
 // stream.cu: one frame of ONE stream as a single cooperative kernel (all layers, grid-wide barriers instead of ~60 launches)
 int rc_stream_frame(rc_state* s, const StepIO& io, int any_first_frame, void* stream);
 bool rc_stream_supported(const rc_state* s);
+// stream2.cu: the same frame with the weights TMA-staged through shared memory and the recurrent halves off the dependency chain
+bool rc_stream2_supported(const rc_state* s);
+int rc_stream2_frame(rc_state* s, const StepIO& io, int t, void* stream);

@@ -370,9 +370,10 @@ for name, variant, start in (('mixed_ff', 'default', 'ff'), ('contact_mixed_ft',
 torch.save(out, sys.argv[1])
 ''' % (repo, os.path.join(repo, 'tests'), golden_dir)
     outs = {}
-    for mode in ('stream', 'multi'):
+    for mode in ('stream', 'multi', 'stream2'):
         env = dict(os.environ)
         env.pop('RC_STREAM_KERNEL', None)
+        env['RC_STREAM2'] = '1' if mode == 'stream2' else '0'
         if mode == 'stream':
             env['RC_STREAM_KERNEL'] = '1'
         f = str(tmp_path / (mode + '.pt'))
@@ -383,6 +384,10 @@ torch.save(out, sys.argv[1])
         assert torch.equal(outs['stream'][name][0], outs['multi'][name][0]), name
         assert torch.equal(outs['stream'][name][1], outs['multi'][name][1]), name
         assert pose_angle(outs['stream'][name][0], g['pose']).max().item() < RAD_TOL
+        # the TMA-staged kernel (stream2.cu, the default single-stream path) sums every dot product in another order (one warp per
+        # hidden unit over shared-memory rows, input and recurrent halves separately): reference bar, and close to the other path
+        assert pose_angle(outs['stream2'][name][0], g['pose']).max().item() < RAD_TOL and (outs['stream2'][name][1] - g['tran']).abs().max().item() < POS_TOL
+        assert pose_angle(outs['stream2'][name][0], outs['multi'][name][0]).max().item() < RAD_TOL
 
 
 def test_ragged_and_degenerate_batches(rb, body, golden_dir):
