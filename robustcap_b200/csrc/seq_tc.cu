@@ -71,6 +71,7 @@ struct alignas(128) SqJob {
     int ldy, kind, net, nt, K, N, H, relu;
     int skipmask, rowmask;
     int ndep1, ndep2, tile0;
+    int xfirst;                    // LSTM: stream the x half of K first and wait for the h_prev producers (dep2) in the middle
     int fshift;                    // the queue hands the job out in frame f for its own frame f + fshift (deferred, non-critical passes: -1)
     SqDep dep1[SQ_MAXDEP], dep2[2];
 };
@@ -547,7 +548,7 @@ rc_seq_kernel(const SqDesc* __restrict__ D, int* __restrict__ ctl, long long* __
                         sq_fence_proxy_async();
                         sq_trace(trace, njobs, fj, j, m, 2);
                     }
-                    const int kb = (i < KH) ? (KB - KH + i) : (i - KH);
+                    const int kb = J.xfirst ? i : ((i < KH) ? (KB - KH + i) : (i - KH));
                     const int s = it % kSqStages;
                     const uint32_t ph = (it / kSqStages) & 1u;
                     mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
@@ -632,7 +633,7 @@ rc_seq_kernel(const SqDesc* __restrict__ D, int* __restrict__ ctl, long long* __
             const int c0 = n0 + part * CW;                       // first accumulator column of this thread
             float cprev[CW / 4];
             const bool rowok = r < D->B;
-            if (lstm && rowok) {                                 // cell state of this thread's units, ahead of the accumulators
+            if (lstm && rowok && !J.xfirst) {                    // cell state of this thread's units, ahead of the accumulators
                 const float* cp = J.C + (size_t)r * H + (c0 >> 2);
 #pragma unroll
                 for (int u = 0; u < CW / 4; u += 4) {
@@ -647,6 +648,14 @@ rc_seq_kernel(const SqDesc* __restrict__ D, int* __restrict__ ctl, long long* __
             tc_fence_after();
             ++gq;
             if (ewarp == 0 && lane == 0) sq_trace(trace, njobs, fj, t.x, m, 3);
+            if (lstm && rowok && J.xfirst) {                     // x-first jobs: the state producers are only known to be done once the MMAs are
+                const float* cp = J.C + (size_t)r * H + (c0 >> 2);
+#pragma unroll
+                for (int u = 0; u < CW / 4; u += 4) {
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(cp + u));
+                    cprev[u] = v.x; cprev[u + 1] = v.y; cprev[u + 2] = v.z; cprev[u + 3] = v.w;
+                }
+            }
             float acc[CW];
             {
                 uint32_t v0[CW], v1[CW];
@@ -977,10 +986,21 @@ int sq_build_jobs(rc_state* s, int bn, SqDesc* d) {
         for (int late = 0; late < 2; ++late) {
             if (jA[i][late] < 0) continue;
             // LSTM-0: h_prev of every pass of the previous frame; readers of the planes it writes; then (second half) its linear1
-            dep1(jA[i][late], jA[i][late ^ 1], 1);
             dep1(jA[i][late], jB[i][0], 2); dep1(jA[i][late], jB[i][1], 2);
             if (i == NET2) dep1(jA[i][late], jINIT, 1);
-            dep2(jA[i][late], jL1[i][late], 0);
+            static const bool xfirst_on = getenv("RC_SEQ_XFIRST") != nullptr;
+            if (xfirst_on && i == NET4 && !late) {
+                // (A/B switch, off: measured no gain — 232 vs 229 us per frame at 128 streams — because the tiles only get a CTA once
+                // the vision updater's tiles have drained.)  rnn4's main pass: its linear1 only needs the frame's inputs and is done long
+                // before the vision updater of the previous frame delivers the last h_prev rows -> x half first, the state dependency in
+                // the middle of the main loop.
+                d->job[jA[i][late]].xfirst = 1;
+                dep1(jA[i][late], jL1[i][late], 0);
+                dep2(jA[i][late], jA[i][late ^ 1], 1);
+            } else {
+                dep1(jA[i][late], jA[i][late ^ 1], 1);
+                dep2(jA[i][late], jL1[i][late], 0);
+            }
             // LSTM-1
             dep1(jB[i][late], jB[i][late ^ 1], 1);
             if (!late) dep1(jB[i][late], jO[i], 2);
