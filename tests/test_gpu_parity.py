@@ -463,9 +463,10 @@ def test_sequence_kernel_matches_grouped(rb, body, B, conf, ragged):
         same = (got[0] == ref[0]).flatten(2).all(dim=2)
         print('sequence kernel vs grouped kernel: %d of %d stream-frames bit-identical' % (int(same.sum()), same.numel()))
         assert same.float().mean().item() > 0.99
-        assert pose_angle(got[0], ref[0]).max().item() < 2e-5 and (got[1] - ref[1]).abs().max().item() < 2e-5
-        # init_net inside the kernel is a per-stream fp32 row job (other summation order than the tensor-core path): tolerance
         valid = torch.ones(B, T, dtype=torch.bool) if lengths is None else (torch.arange(T)[None, :] < lengths[:, None])
+        assert pose_angle(got[0][valid], ref[0][valid]).max().item() < 2e-5 and (got[1] - ref[1]).abs().max().item() < 2e-5
+        assert got[0][~valid].abs().sum().item() == 0                          # frames beyond a stream's length stay zero
+        # init_net inside the kernel is a per-stream fp32 row job (other summation order than the tensor-core path): tolerance
         assert torch.equal(cold[2], ref[2])
         assert pose_angle(cold[0][valid], ref[0][valid]).max().item() < RAD_TOL and (cold[1] - ref[1]).abs().max().item() < POS_TOL
     finally:
