@@ -5,11 +5,13 @@
 // (axis-angle pose [T,72], translation [T,3]) is evaluated with hand-derived derivatives, skinning only the 21 vertices
 // that the 33 MediaPipe points read:
 //   rc_gmm_kernel          block per frame, warp per mixture component: min_m(0.5 d^T P_m d - log w_m) and P_m* d
-//   rc_smplify_fwd_kernel  thread per frame: Rodrigues, FK chain, key points, projection, per-frame loss terms
-//   rc_smplify_bwd_kernel  thread per frame: d loss / d points (incl. the temporal L1 terms that couple t-1, t, t+1),
-//                          back through skinning, the kinematic chain and Rodrigues
+//   rc_smplify_fwd_kernel  warp per frame (lanes = joints / key points / IMU sensors): Rodrigues, FK chain by tree level, key points,
+//                          projection, per-frame loss terms; contiguous global accesses
+//   rc_smplify_bwd_kernel  warp per frame: d loss / d points (incl. the temporal L1 terms that couple t-1, t, t+1), back through
+//                          skinning (lane j gathers over the key points), the kinematic chain (parents gather from their children, level
+//                          by level) and Rodrigues
 //   rc_sum_kernel          deterministic reduction of the per-frame losses
-// The optimiser stays torch.optim.LBFGS (the third-party class the reference itself calls).
+//   rc_smplify_lbfgs_kernel  the optimiser: torch.optim.LBFGS.step + strong Wolfe on the device, the closure above inside
 #include <algorithm>
 #include <vector>
 #include "rc_common.cuh"
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(256) rc_gmm_kernel(const SmplifyConst* __restr
     float q = 0.f;
     for (int i = lane; i < ND; i += 32) {
         float s = 0.f;
-        for (int j = 0; j < ND; ++j) s = fmaf(P[i * ND + j], d[m][j], s);
+        for (int j = 0; j < ND; ++j) s = fmaf(P[j * ND + i], d[m][j], s);     // P is symmetric: column walk = coalesced across the lanes
         pd[m][i] = s;
         q = fmaf(s, d[m][i], q);
     }
@@ -84,7 +86,7 @@ __device__ __forceinline__ void gmm_frame_warp(const SmplifyConst* __restrict__ 
         float q = 0.f;
         for (int i = lane; i < ND; i += 32) {
             float s = 0.f;
-            for (int j = 0; j < ND; ++j) s = fmaf(P[i * ND + j], d[j], s);
+            for (int j = 0; j < ND; ++j) s = fmaf(P[j * ND + i], d[j], s);        // P is symmetric: column walk = coalesced across the lanes
             pd[i] = s;
             q = fmaf(s, d[i], q);
         }
@@ -109,99 +111,6 @@ struct FwdArgs {
                           // 2: the pose pointer holds [T,24,3,3] rotation matrices (get_fitting_loss, value only)
 };
 
-__device__ __forceinline__ void keypoints_from_G(const RcModelConst& M, const float (*G)[12], const float* tran, float* p) {
-    for (int k = 0; k < RC_NKP; ++k) {
-        float o[3];
-        if (M.kp_is_joint[k]) {
-            const int j = M.kp_index[k];
-            for (int r = 0; r < 3; ++r) o[r] = G[j][r * 4 + 3];
-        } else {
-            float Tv[12];
-            for (int e = 0; e < 12; ++e) Tv[e] = 0.f;
-            for (int j = 0; j < RC_NJ; ++j) {
-                const float w = M.kp_w[k][j];
-                if (w != 0.f) {
-                    // skinning transform [R_j | t_j - R_j jrest_j]  (model.py:235)
-                    const float tx = G[j][3] - (G[j][0] * M.jrest[j][0] + G[j][1] * M.jrest[j][1] + G[j][2] * M.jrest[j][2]);
-                    const float ty = G[j][7] - (G[j][4] * M.jrest[j][0] + G[j][5] * M.jrest[j][1] + G[j][6] * M.jrest[j][2]);
-                    const float tz = G[j][11] - (G[j][8] * M.jrest[j][0] + G[j][9] * M.jrest[j][1] + G[j][10] * M.jrest[j][2]);
-                    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Tv[r * 4 + c] = fmaf(w, G[j][r * 4 + c], Tv[r * 4 + c]);
-                    Tv[3] = fmaf(w, tx, Tv[3]); Tv[7] = fmaf(w, ty, Tv[7]); Tv[11] = fmaf(w, tz, Tv[11]);
-                }
-            }
-            for (int r = 0; r < 3; ++r)
-                o[r] = Tv[r * 4] * M.kp_rest[k][0] + Tv[r * 4 + 1] * M.kp_rest[k][1] + Tv[r * 4 + 2] * M.kp_rest[k][2] + Tv[r * 4 + 3];
-        }
-        for (int r = 0; r < 3; ++r) p[k * 3 + r] = o[r] + tran[r];
-    }
-}
-
-__device__ __noinline__ void smplify_fwd_frame(const RcModelConst& M, const FwdArgs& a, int t) {
-    float G[RC_NJ][12];
-    for (int i = 0; i < RC_NJ; ++i) {
-        float R[9], L[12];
-        if (a.rodrigues == 0) rc_batch_rodrigues(a.aa + (size_t)t * 72 + i * 3, R);
-        else if (a.rodrigues == 1) rc_aa_to_mat(a.aa + (size_t)t * 72 + i * 3, R);
-        else { for (int e = 0; e < 9; ++e) R[e] = a.aa[(size_t)t * 216 + i * 9 + e]; }   // mode 2: `aa` holds rotation matrices
-        for (int r = 0; r < 3; ++r) { L[r * 4] = R[r * 3]; L[r * 4 + 1] = R[r * 3 + 1]; L[r * 4 + 2] = R[r * 3 + 2]; L[r * 4 + 3] = M.bone[i][r]; }
-        if (i == 0) for (int e = 0; e < 12; ++e) G[0][e] = L[e];
-        else rc_rigid_mul(G[M.parent[i]], L, G[i]);
-    }
-    float tr[3] = {a.tran[t * 3], a.tran[t * 3 + 1], a.tran[t * 3 + 2]};
-    float p[99];
-    keypoints_from_G(M, G, tr, p);
-    float* Gs = a.G + (size_t)t * 288;
-    for (int i = 0; i < RC_NJ; ++i) for (int e = 0; e < 12; ++e) Gs[i * 12 + e] = G[i][e];
-    float K[9];
-    for (int e = 0; e < 9; ++e) K[e] = a.camk[e];
-    float loss = 0.f;
-    // re-projection (losses.py:36-46): conf^2 * sum_xy gmof(K (p / p_z) - j2d, 100)
-    for (int k = 0; k < RC_NKP; ++k) {
-        const float x = p[k * 3] / p[k * 3 + 2], y = p[k * 3 + 1] / p[k * 3 + 2], z = p[k * 3 + 2] / p[k * 3 + 2];
-        const float u = K[0] * x + K[1] * y + K[2] * z, v = K[3] * x + K[4] * y + K[5] * z;
-        a.p[(size_t)t * 99 + k * 3] = p[k * 3]; a.p[(size_t)t * 99 + k * 3 + 1] = p[k * 3 + 1]; a.p[(size_t)t * 99 + k * 3 + 2] = p[k * 3 + 2];
-        a.proj[(size_t)t * 66 + k * 2] = u; a.proj[(size_t)t * 66 + k * 2 + 1] = v;
-        const float c = a.conf[(size_t)t * 33 + k];
-        const float ru = u - a.j2d[(size_t)t * 66 + k * 2], rv = v - a.j2d[(size_t)t * 66 + k * 2 + 1];
-        const float e = (1e4f * ru * ru) / (1e4f + ru * ru) + (1e4f * rv * rv) / (1e4f + rv * rv);
-        const float rl = c * c * e;
-        if (a.reproj) a.reproj[(size_t)t * 33 + k] = rl;
-        loss += rl;
-    }
-    // 3-D term (losses.py:32-34): sum_i |(p_i - p_0) - (ref_i - ref_0)|^2
-    for (int k = 1; k < RC_NKP; ++k)
-        for (int r = 0; r < 3; ++r) {
-            const float d = (p[k * 3 + r] - p[r]) - (a.ref3d[(size_t)t * 99 + k * 3 + r] - a.ref3d[(size_t)t * 99 + r]);
-            loss = fmaf(d, d, loss);
-        }
-    // GMM prior (0.1^2) and angle prior (15.2^2 * exp(+-x)^2)   (losses.py:49-54)
-    if (a.rodrigues != 2) {
-        loss = fmaf(0.01f, a.prior[t], loss);
-        for (int q = 0; q < 4; ++q) {
-            const float e = expf(a.aa[(size_t)t * 72 + 3 + c_angle_idx[q]] * c_angle_sign[q]);
-            loss = fmaf(231.04f, e * e, loss);
-        }
-    }
-    // IMU term (losses.py:39-40), value only: 0.5^2 |aa(imu_ori) - aa(R_glb[ji_mask])|^2, cv2.Rodrigues semantics.
-    // losses.py:63 broadcasts the sum over frames onto every frame; the caller multiplies by T (see rc_smplify_loss_grad).
-    float imu = 0.f;
-    for (int s = 0; s < 6; ++s) {
-        const int j = c_ji_mask[s];
-        float R[9], v[3];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = G[j][r * 4 + c];
-        rc_mat_to_aa(R, v);
-        for (int r = 0; r < 3; ++r) { const float d = a.imu_aa[(size_t)t * 18 + s * 3 + r] - v[r]; imu = fmaf(d, d, imu); }
-    }
-    a.lossf[t] = loss;
-    a.lossf[a.T + t] = 0.25f * imu;
-}
-
-__global__ void __launch_bounds__(32) rc_smplify_fwd_kernel(const RcModelConst* __restrict__ Mp, FwdArgs a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.T) return;
-    smplify_fwd_frame(*Mp, a, t);
-}
-
 // ---- backward ----------------------------------------------------------------------------------------------------------
 struct BwdArgs {
     const float *aa, *j2d, *conf, *camk, *ref3d, *G, *p, *proj, *gprior;
@@ -209,120 +118,237 @@ struct BwdArgs {
     int T;
 };
 
-__device__ __noinline__ void smplify_bwd_frame(const RcModelConst& M, const BwdArgs& a, int t) {
-    const float* p = a.p + (size_t)t * 99;
-    const float* pr = a.proj + (size_t)t * 66;
-    float K[9];
-    for (int e = 0; e < 9; ++e) K[e] = a.camk[e];
-    float gp[99];
-    float smooth = 0.f;
-    float g0[3] = {0.f, 0.f, 0.f};
-    for (int k = 0; k < RC_NKP; ++k) {
+
+// ---- warp-per-frame closure ---------------------------------------------------------------------------------------------------
+// One warp evaluates one frame: lanes = joints (Rodrigues, chain by tree level, Rodrigues backward) / key points (skinning of the 21
+// vertices, projection, loss terms, their gradients) / IMU sensors (the six cv2.Rodrigues log maps); the per-frame arrays live in
+// shared memory, global reads and writes are contiguous across the warp.  Same formulas as the scalar derivation they replace.
+struct SmpWarp {
+    float L[RC_NJ][12];        // local transforms [R | bone]; backward: reused for gR (9) + gt (3) per joint
+    float G[RC_NJ][12];        // global transforms
+    float p[RC_NKP][3];        // key points
+    float gp[RC_NKP][3];       // d loss / d key point
+    float red[4];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// key point k from the global transforms (model.py:235-241 restricted to one vertex / joint)
+__device__ __forceinline__ void keypoint_from_G(const RcModelConst& M, const float (*G)[12], const float* tran, int k, float* o) {
+    if (M.kp_is_joint[k]) {
+        const int j = M.kp_index[k];
+        for (int r = 0; r < 3; ++r) o[r] = G[j][r * 4 + 3] + tran[r];
+        return;
+    }
+    float Tv[12];
+    for (int e = 0; e < 12; ++e) Tv[e] = 0.f;
+    for (int j = 0; j < RC_NJ; ++j) {
+        const float w = M.kp_w[k][j];
+        if (w != 0.f) {
+            const float tx = G[j][3] - (G[j][0] * M.jrest[j][0] + G[j][1] * M.jrest[j][1] + G[j][2] * M.jrest[j][2]);
+            const float ty = G[j][7] - (G[j][4] * M.jrest[j][0] + G[j][5] * M.jrest[j][1] + G[j][6] * M.jrest[j][2]);
+            const float tz = G[j][11] - (G[j][8] * M.jrest[j][0] + G[j][9] * M.jrest[j][1] + G[j][10] * M.jrest[j][2]);
+            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Tv[r * 4 + c] = fmaf(w, G[j][r * 4 + c], Tv[r * 4 + c]);
+            Tv[3] = fmaf(w, tx, Tv[3]); Tv[7] = fmaf(w, ty, Tv[7]); Tv[11] = fmaf(w, tz, Tv[11]);
+        }
+    }
+    for (int r = 0; r < 3; ++r)
+        o[r] = Tv[r * 4] * M.kp_rest[k][0] + Tv[r * 4 + 1] * M.kp_rest[k][1] + Tv[r * 4 + 2] * M.kp_rest[k][2] + Tv[r * 4 + 3] + tran[r];
+}
+
+__device__ __forceinline__ void smplify_fwd_warp(const RcModelConst& M, const FwdArgs& a, int t, SmpWarp& S, int lane) {
+    // local transforms, one joint per lane
+    if (lane < RC_NJ) {
+        float R[9];
+        if (a.rodrigues == 0) rc_batch_rodrigues(a.aa + (size_t)t * 72 + lane * 3, R);
+        else if (a.rodrigues == 1) rc_aa_to_mat(a.aa + (size_t)t * 72 + lane * 3, R);
+        else { for (int e = 0; e < 9; ++e) R[e] = a.aa[(size_t)t * 216 + lane * 9 + e]; }
+        for (int r = 0; r < 3; ++r) { S.L[lane][r * 4] = R[r * 3]; S.L[lane][r * 4 + 1] = R[r * 3 + 1]; S.L[lane][r * 4 + 2] = R[r * 3 + 2]; S.L[lane][r * 4 + 3] = M.bone[lane][r]; }
+        if (lane == 0) for (int e = 0; e < 12; ++e) S.G[0][e] = S.L[0][e];
+    }
+    __syncwarp();
+    for (int lev = 1; lev <= M.max_depth; ++lev) {                         // chain by tree level (spatial.py:224-249)
+        if (lane < RC_NJ && M.depth[lane] == lev) rc_rigid_mul(S.G[M.parent[lane]], S.L[lane], S.G[lane]);
+        __syncwarp();
+    }
+    const float tr[3] = {a.tran[t * 3], a.tran[t * 3 + 1], a.tran[t * 3 + 2]};
+    for (int k = lane; k < RC_NKP; k += 32) keypoint_from_G(M, S.G, tr, k, S.p[k]);
+    __syncwarp();
+    for (int e = lane; e < RC_NJ * 12; e += 32) a.G[(size_t)t * 288 + e] = S.G[e / 12][e % 12];
+    for (int e = lane; e < RC_NKP * 3; e += 32) a.p[(size_t)t * 99 + e] = S.p[e / 3][e % 3];
+    float K[6];
+    for (int e = 0; e < 6; ++e) K[e] = a.camk[e];
+    float loss = 0.f;
+    for (int k = lane; k < RC_NKP; k += 32) {
+        const float* p = S.p[k];
+        // re-projection (losses.py:36-46): conf^2 * sum_xy gmof(K (p / p_z) - j2d, 100)
+        const float x = p[0] / p[2], y = p[1] / p[2], z = p[2] / p[2];
+        const float u = K[0] * x + K[1] * y + K[2] * z, v = K[3] * x + K[4] * y + K[5] * z;
+        a.proj[(size_t)t * 66 + k * 2] = u; a.proj[(size_t)t * 66 + k * 2 + 1] = v;
+        const float c = a.conf[(size_t)t * 33 + k];
+        const float ru = u - a.j2d[(size_t)t * 66 + k * 2], rv = v - a.j2d[(size_t)t * 66 + k * 2 + 1];
+        const float e = (1e4f * ru * ru) / (1e4f + ru * ru) + (1e4f * rv * rv) / (1e4f + rv * rv);
+        const float rl = c * c * e;
+        if (a.reproj) a.reproj[(size_t)t * 33 + k] = rl;
+        loss += rl;
+        // 3-D term (losses.py:32-34): sum_i |(p_i - p_0) - (ref_i - ref_0)|^2
+        if (k >= 1)
+            for (int r = 0; r < 3; ++r) {
+                const float d = (p[r] - S.p[0][r]) - (a.ref3d[(size_t)t * 99 + k * 3 + r] - a.ref3d[(size_t)t * 99 + r]);
+                loss = fmaf(d, d, loss);
+            }
+    }
+    // IMU term (losses.py:39-40), value only: 0.5^2 |aa(imu_ori) - aa(R_glb[ji_mask])|^2, cv2.Rodrigues semantics, one sensor per lane
+    float imu = 0.f;
+    if (lane < 6) {
+        const int j = c_ji_mask[lane];
+        float R[9], v[3];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r * 3 + c] = S.G[j][r * 4 + c];
+        rc_mat_to_aa(R, v);
+        for (int r = 0; r < 3; ++r) { const float d = a.imu_aa[(size_t)t * 18 + lane * 3 + r] - v[r]; imu = fmaf(d, d, imu); }
+    }
+    // GMM prior (0.1^2) and angle prior (15.2^2 * exp(+-x)^2)   (losses.py:49-54), lanes 8..11
+    if (a.rodrigues != 2 && lane >= 8 && lane < 12) {
+        const int q = lane - 8;
+        const float e = expf(a.aa[(size_t)t * 72 + 3 + c_angle_idx[q]] * c_angle_sign[q]);
+        loss = fmaf(231.04f, e * e, loss);
+    }
+    loss = warp_sum(loss);
+    imu = warp_sum(imu);
+    if (lane == 0) {
+        if (a.rodrigues != 2) loss = fmaf(0.01f, a.prior[t], loss);
+        a.lossf[t] = loss;
+        a.lossf[a.T + t] = 0.25f * imu;
+    }
+}
+
+__device__ __forceinline__ void smplify_bwd_warp(const RcModelConst& M, const BwdArgs& a, int t, SmpWarp& S, int lane) {
+    float K[6];
+    for (int e = 0; e < 6; ++e) K[e] = a.camk[e];
+    // this frame's transforms and points back into shared memory (coalesced)
+    for (int e = lane; e < RC_NJ * 12; e += 32) S.G[e / 12][e % 12] = a.G[(size_t)t * 288 + e];
+    for (int e = lane; e < RC_NKP * 3; e += 32) S.p[e / 3][e % 3] = a.p[(size_t)t * 99 + e];
+    __syncwarp();
+    float smooth = 0.f, g0[3] = {0.f, 0.f, 0.f}, gtr[3] = {0.f, 0.f, 0.f};
+    for (int k = lane; k < RC_NKP; k += 32) {
+        const float* p = S.p[k];
+        const float* pr = a.proj + (size_t)t * 66 + k * 2;
         const float c = a.conf[(size_t)t * 33 + k], c2 = c * c;
-        // d gmof(r)/dr = 2 r s^4 / (s^2 + r^2)^2
-        const float ru = pr[k * 2] - a.j2d[(size_t)t * 66 + k * 2], rv = pr[k * 2 + 1] - a.j2d[(size_t)t * 66 + k * 2 + 1];
+        const float ru = pr[0] - a.j2d[(size_t)t * 66 + k * 2], rv = pr[1] - a.j2d[(size_t)t * 66 + k * 2 + 1];
         const float du = 1e4f + ru * ru, dv = 1e4f + rv * rv;
         float gu = c2 * 2.f * ru * 1e8f / (du * du), gv = c2 * 2.f * rv * 1e8f / (dv * dv);
         float g3[3] = {0.f, 0.f, 0.f};
-        // temporal L1 terms (losses.py:66-84): frame t pulls towards t-1 with conf_t^2, frame t+1 pulls on t with conf_{t+1}^2
-        if (t >= 1) {
-            const float* pp = a.p + (size_t)(t - 1) * 99;
-            const float* qq = a.proj + (size_t)(t - 1) * 66;
+        if (t >= 1) {                                                       // temporal L1 terms (losses.py:66-84)
+            const float* pp = a.p + (size_t)(t - 1) * 99 + k * 3;
+            const float* qq = a.proj + (size_t)(t - 1) * 66 + k * 2;
             for (int r = 0; r < 2; ++r) {
-                const float d = pr[k * 2 + r] - qq[k * 2 + r];
+                const float d = pr[r] - qq[r];
                 smooth = fmaf(1e-4f * c2, fabsf(d), smooth);
-                const float s = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-                if (r == 0) gu = fmaf(1e-4f * c2, s, gu); else gv = fmaf(1e-4f * c2, s, gv);
+                const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+                if (r == 0) gu = fmaf(1e-4f * c2, sg, gu); else gv = fmaf(1e-4f * c2, sg, gv);
             }
             for (int r = 0; r < 3; ++r) {
-                const float d = p[k * 3 + r] - pp[k * 3 + r];
+                const float d = p[r] - pp[r];
                 smooth = fmaf(c2, fabsf(d), smooth);
                 g3[r] += c2 * ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
             }
         }
         if (t + 1 < a.T) {
             const float cn = a.conf[(size_t)(t + 1) * 33 + k], cn2 = cn * cn;
-            const float* pn = a.p + (size_t)(t + 1) * 99;
-            const float* qn = a.proj + (size_t)(t + 1) * 66;
+            const float* pn = a.p + (size_t)(t + 1) * 99 + k * 3;
+            const float* qn = a.proj + (size_t)(t + 1) * 66 + k * 2;
             for (int r = 0; r < 2; ++r) {
-                const float d = qn[k * 2 + r] - pr[k * 2 + r];
-                const float s = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
-                if (r == 0) gu = fmaf(-1e-4f * cn2, s, gu); else gv = fmaf(-1e-4f * cn2, s, gv);
+                const float d = qn[r] - pr[r];
+                const float sg = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+                if (r == 0) gu = fmaf(-1e-4f * cn2, sg, gu); else gv = fmaf(-1e-4f * cn2, sg, gv);
             }
             for (int r = 0; r < 3; ++r) {
-                const float d = pn[k * 3 + r] - p[k * 3 + r];
+                const float d = pn[r] - p[r];
                 g3[r] -= cn2 * ((d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f));
             }
         }
-        // (u, v) = K[:2] (x/z, y/z, z/z): d/dx = K?0 / z, d/dy = K?1 / z, d/dz = -(K?0 x + K?1 y) / z^2  (the z/z term is constant 1
-        // for autograd too: d(z/z)/dz = 1/z - z/z^2 = 0)
-        const float x = p[k * 3], y = p[k * 3 + 1], z = p[k * 3 + 2], iz = 1.f / z;
-        const float gx = (gu * K[0] + gv * K[3]) * iz, gy = (gu * K[1] + gv * K[4]) * iz;
-        const float gz = -(gu * (K[0] * x + K[1] * y) + gv * (K[3] * x + K[4] * y)) * iz * iz;
-        g3[0] += gx; g3[1] += gy; g3[2] += gz;
+        const float x = p[0], y = p[1], z = p[2], iz = 1.f / z;
+        g3[0] += (gu * K[0] + gv * K[3]) * iz;
+        g3[1] += (gu * K[1] + gv * K[4]) * iz;
+        g3[2] += -(gu * (K[0] * x + K[1] * y) + gv * (K[3] * x + K[4] * y)) * iz * iz;
         if (k >= 1) {
             for (int r = 0; r < 3; ++r) {
-                const float d = (p[k * 3 + r] - p[r]) - (a.ref3d[(size_t)t * 99 + k * 3 + r] - a.ref3d[(size_t)t * 99 + r]);
+                const float d = (p[r] - S.p[0][r]) - (a.ref3d[(size_t)t * 99 + k * 3 + r] - a.ref3d[(size_t)t * 99 + r]);
                 g3[r] = fmaf(2.f, d, g3[r]);
                 g0[r] = fmaf(-2.f, d, g0[r]);
             }
         }
-        gp[k * 3] = g3[0]; gp[k * 3 + 1] = g3[1]; gp[k * 3 + 2] = g3[2];
+        for (int r = 0; r < 3; ++r) S.gp[k][r] = g3[r];
     }
-    for (int r = 0; r < 3; ++r) gp[r] += g0[r];
-    a.lossf[2 * a.T + t] = smooth;
-
-    // points -> global joint transforms
-    const float* G = a.G + (size_t)t * 288;
-    float gR[RC_NJ][9], gt[RC_NJ][3];
-    for (int j = 0; j < RC_NJ; ++j) { for (int e = 0; e < 9; ++e) gR[j][e] = 0.f; gt[j][0] = gt[j][1] = gt[j][2] = 0.f; }
-    float gtr[3] = {0.f, 0.f, 0.f};
-    for (int k = 0; k < RC_NKP; ++k) {
-        const float* g = gp + k * 3;
-        for (int r = 0; r < 3; ++r) gtr[r] += g[r];
-        if (M.kp_is_joint[k]) {
-            const int j = M.kp_index[k];
-            for (int r = 0; r < 3; ++r) gt[j][r] += g[r];
-        } else {
-            for (int j = 0; j < RC_NJ; ++j) {
+    smooth = warp_sum(smooth);
+    for (int r = 0; r < 3; ++r) g0[r] = warp_sum(g0[r]);
+    __syncwarp();
+    if (lane == 0) { for (int r = 0; r < 3; ++r) S.gp[0][r] += g0[r]; a.lossf[2 * a.T + t] = smooth; }
+    __syncwarp();
+    for (int k = lane; k < RC_NKP; k += 32) for (int r = 0; r < 3; ++r) gtr[r] += S.gp[k][r];
+    for (int r = 0; r < 3; ++r) gtr[r] = warp_sum(gtr[r]);
+    // points -> global joint transforms: lane j gathers over the key points (S.L[j] = [gR (9) | gt (3)])
+    if (lane < RC_NJ) {
+        const int j = lane;
+        float gR[9], gt[3] = {0.f, 0.f, 0.f};
+        for (int e = 0; e < 9; ++e) gR[e] = 0.f;
+        for (int k = 0; k < RC_NKP; ++k) {
+            const float* g = S.gp[k];
+            if (M.kp_is_joint[k]) {
+                if (M.kp_index[k] == j) for (int r = 0; r < 3; ++r) gt[r] += g[r];
+            } else {
                 const float w = M.kp_w[k][j];
                 if (w != 0.f) {
-                    // p += w (R_j (v - jrest_j) + t_j)
                     const float dx = M.kp_rest[k][0] - M.jrest[j][0], dy = M.kp_rest[k][1] - M.jrest[j][1], dz = M.kp_rest[k][2] - M.jrest[j][2];
                     for (int r = 0; r < 3; ++r) {
                         const float wg = w * g[r];
-                        gR[j][r * 3] = fmaf(wg, dx, gR[j][r * 3]); gR[j][r * 3 + 1] = fmaf(wg, dy, gR[j][r * 3 + 1]); gR[j][r * 3 + 2] = fmaf(wg, dz, gR[j][r * 3 + 2]);
-                        gt[j][r] += wg;
+                        gR[r * 3] = fmaf(wg, dx, gR[r * 3]); gR[r * 3 + 1] = fmaf(wg, dy, gR[r * 3 + 1]); gR[r * 3 + 2] = fmaf(wg, dz, gR[r * 3 + 2]);
+                        gt[r] += wg;
                     }
                 }
             }
         }
+        for (int e = 0; e < 9; ++e) S.L[j][e] = gR[e];
+        for (int r = 0; r < 3; ++r) S.L[j][9 + r] = gt[r];
     }
-    // chain, leaves to root: R_j = R_p Rl_j, t_j = R_p b_j + t_p
-    float gaa[72];
-    for (int j = RC_NJ - 1; j >= 0; --j) {
-        float gRl[9];
-        float Rl[9];
-        const int pj = M.parent[j];
-        if (j > 0) {
-            const float* Gp = G + pj * 12;
-            const float* Gj = G + j * 12;
-            // Rl_j = R_p^T R_j ; gRl = R_p^T gR_j ; gR_p += gR_j Rl_j^T + gt_j b_j^T ; gt_p += gt_j
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) {
-                    Rl[r * 3 + c] = Gp[0 * 4 + r] * Gj[0 * 4 + c] + Gp[1 * 4 + r] * Gj[1 * 4 + c] + Gp[2 * 4 + r] * Gj[2 * 4 + c];
-                    gRl[r * 3 + c] = Gp[0 * 4 + r] * gR[j][0 * 3 + c] + Gp[1 * 4 + r] * gR[j][1 * 3 + c] + Gp[2 * 4 + r] * gR[j][2 * 3 + c];
-                }
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) {
-                    const float v = gR[j][r * 3] * Rl[c * 3] + gR[j][r * 3 + 1] * Rl[c * 3 + 1] + gR[j][r * 3 + 2] * Rl[c * 3 + 2];
-                    gR[pj][r * 3 + c] += v + gt[j][r] * M.bone[j][c];
-                }
-            for (int r = 0; r < 3; ++r) gt[pj][r] += gt[j][r];
-        } else {
-            for (int e = 0; e < 9; ++e) gRl[e] = gR[0][e];
+    __syncwarp();
+    // chain, leaves to root, one tree level at a time: a parent gathers from its children
+    //   R_c = R_p Rl_c, t_c = R_p b_c + t_p  =>  gR_p += gR_c Rl_c^T + gt_c b_c^T, gt_p += gt_c
+    for (int lev = M.max_depth; lev >= 1; --lev) {
+        if (lane < RC_NJ && M.depth[lane] == lev - 1) {
+            const int pj = lane;
+            for (int c = 1; c < RC_NJ; ++c) {
+                if (M.parent[c] != pj || M.depth[c] != lev) continue;
+                const float* Gp = S.G[pj];
+                const float* Gc = S.G[c];
+                float Rl[9];
+                for (int r = 0; r < 3; ++r)
+                    for (int q = 0; q < 3; ++q) Rl[r * 3 + q] = Gp[0 * 4 + r] * Gc[0 * 4 + q] + Gp[1 * 4 + r] * Gc[1 * 4 + q] + Gp[2 * 4 + r] * Gc[2 * 4 + q];
+                for (int r = 0; r < 3; ++r)
+                    for (int q = 0; q < 3; ++q) {
+                        const float v = S.L[c][r * 3] * Rl[q * 3] + S.L[c][r * 3 + 1] * Rl[q * 3 + 1] + S.L[c][r * 3 + 2] * Rl[q * 3 + 2];
+                        S.L[pj][r * 3 + q] += v + S.L[c][9 + r] * M.bone[c][q];
+                    }
+                for (int r = 0; r < 3; ++r) S.L[pj][9 + r] += S.L[c][9 + r];
+            }
         }
-        // Rodrigues backward: R = I + sin(th) K(d) + (1 - cos(th)) K(d)^2, th = |v + 1e-8|, d = v / th
+        __syncwarp();
+    }
+    // Rodrigues backward, one joint per lane: R = I + sin(th) K(d) + (1 - cos(th)) K(d)^2, th = |v + 1e-8|, d = v / th
+    if (lane < RC_NJ) {
+        const int j = lane;
+        float gRl[9];
+        if (j > 0) {
+            const float* Gp = S.G[M.parent[j]];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) gRl[r * 3 + c] = Gp[0 * 4 + r] * S.L[j][0 * 3 + c] + Gp[1 * 4 + r] * S.L[j][1 * 3 + c] + Gp[2 * 4 + r] * S.L[j][2 * 3 + c];
+        } else {
+            for (int e = 0; e < 9; ++e) gRl[e] = S.L[0][e];
+        }
         const float* v = a.aa + (size_t)t * 72 + j * 3;
         const float e0 = v[0] + 1e-8f, e1 = v[1] + 1e-8f, e2 = v[2] + 1e-8f;
         const float th = sqrtf(e0 * e0 + e1 * e1 + e2 * e2);
@@ -334,7 +360,6 @@ __device__ __noinline__ void smplify_bwd_frame(const RcModelConst& M, const BwdA
         float gs = 0.f, go = 0.f;
         for (int e = 0; e < 9; ++e) { gs = fmaf(gRl[e], Km[e], gs); go = fmaf(gRl[e], KK[e], go); }
         const float gth = gs * cs + go * sn;
-        // gK = sn gRl + om (gRl K^T + K^T gRl)
         float gK[9];
         for (int r = 0; r < 3; ++r)
             for (int c = 0; c < 3; ++c) {
@@ -345,27 +370,41 @@ __device__ __noinline__ void smplify_bwd_frame(const RcModelConst& M, const BwdA
         const float gd0 = gK[7] - gK[5], gd1 = gK[2] - gK[6], gd2 = gK[3] - gK[1];
         const float gdv = gd0 * v[0] + gd1 * v[1] + gd2 * v[2];
         const float ith = 1.f / th, ith3 = ith * ith * ith;
-        gaa[j * 3 + 0] = gd0 * ith - gdv * e0 * ith3 + gth * e0 * ith;
-        gaa[j * 3 + 1] = gd1 * ith - gdv * e1 * ith3 + gth * e1 * ith;
-        gaa[j * 3 + 2] = gd2 * ith - gdv * e2 * ith3 + gth * e2 * ith;
+        S.p[j][0] = gd0 * ith - gdv * e0 * ith3 + gth * e0 * ith;            // S.p is free now: gaa staging
+        S.p[j][1] = gd1 * ith - gdv * e1 * ith3 + gth * e1 * ith;
+        S.p[j][2] = gd2 * ith - gdv * e2 * ith3 + gth * e2 * ith;
     }
+    __syncwarp();
+    float* gaa = &S.p[0][0];                                               // [72]
     // priors act directly on pose[3:]
-    for (int q = 0; q < ND; ++q) gaa[3 + q] = fmaf(0.01f, a.gprior[(size_t)t * ND + q], gaa[3 + q]);
-    for (int q = 0; q < 4; ++q) {
-        const float sg = c_angle_sign[q];
-        const float e = expf(a.aa[(size_t)t * 72 + 3 + c_angle_idx[q]] * sg);
-        gaa[3 + c_angle_idx[q]] = fmaf(231.04f * 2.f * sg, e * e, gaa[3 + c_angle_idx[q]]);
+    for (int q = lane; q < ND; q += 32) gaa[3 + q] = fmaf(0.01f, a.gprior[(size_t)t * ND + q], gaa[3 + q]);
+    __syncwarp();
+    if (lane < 4) {
+        const float sg = c_angle_sign[lane];
+        const float e = expf(a.aa[(size_t)t * 72 + 3 + c_angle_idx[lane]] * sg);
+        gaa[3 + c_angle_idx[lane]] = fmaf(231.04f * 2.f * sg, e * e, gaa[3 + c_angle_idx[lane]]);
     }
-    for (int e = 0; e < 72; ++e) a.gaa[(size_t)t * 72 + e] = gaa[e];
-    for (int r = 0; r < 3; ++r) a.gtran[(size_t)t * 3 + r] = gtr[r];
+    __syncwarp();
+    for (int e = lane; e < 72; e += 32) a.gaa[(size_t)t * 72 + e] = gaa[e];
+    if (lane < 3) a.gtran[(size_t)t * 3 + lane] = gtr[lane];
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(32) rc_smplify_bwd_kernel(const RcModelConst* __restrict__ Mp, BwdArgs a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kSmpWarps = 8;
+__global__ void __launch_bounds__(kSmpWarps * 32) rc_smplify_fwd_kernel(const RcModelConst* __restrict__ Mp, FwdArgs a) {
+    __shared__ SmpWarp S[kSmpWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kSmpWarps + warp;
     if (t >= a.T) return;
-    smplify_bwd_frame(*Mp, a, t);
+    smplify_fwd_warp(*Mp, a, t, S[warp], lane);
 }
-
+__global__ void __launch_bounds__(kSmpWarps * 32) rc_smplify_bwd_kernel(const RcModelConst* __restrict__ Mp, BwdArgs a) {
+    __shared__ SmpWarp S[kSmpWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * kSmpWarps + warp;
+    if (t >= a.T) return;
+    smplify_bwd_warp(*Mp, a, t, S[warp], lane);
+}
 
 // ---- device-resident L-BFGS (torch.optim.LBFGS.step with line_search_fn='strong_wolfe', temporal_smplify.py:151-166) ----------------
 // ONE thread block per sequence runs the whole optimisation: closure evaluations (GMM prior -> forward -> backward -> loss sum, the
@@ -460,7 +499,7 @@ __device__ __forceinline__ float lb_cubic(float x1, float f1, float g1, float x2
 }
 
 // closure: loss and gradient at x (aa | tran) -> g; every thread returns the loss
-__device__ float lb_eval(const RcModelConst& M, const LbfgsArgs& a, int seq, const float* x, float* g, LbShared& sh) {
+__device__ float lb_eval(const RcModelConst& M, const LbfgsArgs& a, int seq, const float* x, float* g, LbShared& sh, SmpWarp* sw) {
     const int T = a.T, tid = threadIdx.x, nt = blockDim.x, warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
     const size_t so = (size_t)seq * T;
     float* prior = a.prior + so;
@@ -472,12 +511,12 @@ __device__ float lb_eval(const RcModelConst& M, const LbfgsArgs& a, int seq, con
     f.aa = x; f.tran = x + (size_t)T * 72; f.j2d = a.j2d + so * 66; f.conf = a.conf + so * 33; f.camk = a.camk + (size_t)seq * a.camk_stride;
     f.ref3d = a.ref3d + so * 99; f.imu_aa = a.imu_aa + so * 18; f.prior = prior;
     f.G = a.G + so * 288; f.p = a.p + so * 99; f.proj = a.proj + so * 66; f.lossf = a.lossf + so * 3; f.reproj = nullptr; f.T = T; f.rodrigues = 0;
-    for (int t = tid; t < T; t += nt) smplify_fwd_frame(M, f, t);
+    for (int t = warp; t < T; t += nw) smplify_fwd_warp(M, f, t, sw[warp], lane);
     __syncthreads();
     BwdArgs b;
     b.aa = x; b.j2d = f.j2d; b.conf = f.conf; b.camk = f.camk; b.ref3d = f.ref3d; b.G = f.G; b.p = f.p; b.proj = f.proj; b.gprior = gprior;
     b.lossf = f.lossf; b.gaa = g; b.gtran = g + (size_t)T * 72; b.T = T;
-    for (int t = tid; t < T; t += nt) smplify_bwd_frame(M, b, t);
+    for (int t = warp; t < T; t += nw) smplify_bwd_warp(M, b, t, sw[warp], lane);
     __syncthreads();
     // loss = sum_t (frame + smooth) + T * sum_t imu: the reduction order of rc_smplify_sum_kernel (256 strided partial sums, tree)
     if (tid < 256) {
@@ -498,7 +537,9 @@ __device__ float lb_eval(const RcModelConst& M, const LbfgsArgs& a, int seq, con
 }
 
 __global__ void __launch_bounds__(kLbThreadsMax) rc_smplify_lbfgs_kernel(const RcModelConst* __restrict__ Mp, const LbfgsArgs a) {
-    __shared__ LbShared sh;
+    extern __shared__ __align__(16) unsigned char lb_smem[];
+    LbShared& sh = *reinterpret_cast<LbShared*>(lb_smem);
+    SmpWarp* sw = reinterpret_cast<SmpWarp*>(lb_smem + ((sizeof(LbShared) + 15) / 16) * 16);
     const RcModelConst& M = *Mp;
     const int seq = blockIdx.x, n = a.n, T = a.T;
     const int nvec = LB_NFIXED + 2 * a.hist;
@@ -515,7 +556,7 @@ __global__ void __launch_bounds__(kLbThreadsMax) rc_smplify_lbfgs_kernel(const R
     int nh = 0;
     float H_diag = 1.f, t = 0.f;
 
-    float loss = lb_eval(M, a, seq, X, vec(LB_G), sh);
+    float loss = lb_eval(M, a, seq, X, vec(LB_G), sh, sw);
     const float first_loss = loss;
     int evals = 1, n_iter = 0;
     bool stop = lb_absmax(vec(LB_G), 1.f, n, sh) <= tol_grad;
@@ -573,7 +614,7 @@ __global__ void __launch_bounds__(kLbThreadsMax) rc_smplify_lbfgs_kernel(const R
         const float d_norm = lb_absmax(D, 1.f, n, sh);
         float* GN = vec(LB_GN);
         lb_axpy_to(X, XI, t, D, n);
-        float f_new = lb_eval(M, a, seq, X, GN, sh);
+        float f_new = lb_eval(M, a, seq, X, GN, sh, sw);
         int ls_evals = 1;
         float gtd_new = lb_dot(GN, D, n, sh);
         float t_prev = 0.f, f_prev = f, gtd_prev = gtd;
@@ -598,7 +639,7 @@ __global__ void __launch_bounds__(kLbThreadsMax) rc_smplify_lbfgs_kernel(const R
             t_prev = tmp; f_prev = f_new; gtd_prev = gtd_new;
             lb_copy(vec(LB_GPREV), GN, n);
             lb_axpy_to(X, XI, t, D, n);
-            f_new = lb_eval(M, a, seq, X, GN, sh);
+            f_new = lb_eval(M, a, seq, X, GN, sh, sw);
             ++ls_evals;
             gtd_new = lb_dot(GN, D, n, sh);
             ++ls_iter;
@@ -621,7 +662,7 @@ __global__ void __launch_bounds__(kLbThreadsMax) rc_smplify_lbfgs_kernel(const R
                 } else insuf = true;
             } else insuf = false;
             lb_axpy_to(X, XI, t, D, n);
-            f_new = lb_eval(M, a, seq, X, GN, sh);
+            f_new = lb_eval(M, a, seq, X, GN, sh, sw);
             ++ls_evals;
             gtd_new = lb_dot(GN, D, n, sh);
             ++ls_iter;
@@ -735,13 +776,13 @@ int rc_smplify_loss_grad(rc_smplify* s, const float* aa, const float* tran, cons
     FwdArgs f;
     f.aa = aa; f.tran = tran; f.j2d = j2d; f.conf = conf; f.camk = camk; f.ref3d = ref3d; f.imu_aa = imu_aa; f.prior = s->d_prior;
     f.G = s->d_G; f.p = s->d_p; f.proj = s->d_proj; f.lossf = s->d_lossf; f.reproj = reproj; f.T = T; f.rodrigues = rodrigues;
-    RC_LAUNCH(rc_smplify_fwd_kernel, rc_cdiv(T, 32), 32, 0, stream, s->model->d_const, f);
+    RC_LAUNCH(rc_smplify_fwd_kernel, rc_cdiv(T, kSmpWarps), kSmpWarps * 32, 0, stream, s->model->d_const, f);
     RC_CHECK_LAUNCH();
     if (grad_aa) {
         BwdArgs b;
         b.aa = aa; b.j2d = j2d; b.conf = conf; b.camk = camk; b.ref3d = ref3d; b.G = s->d_G; b.p = s->d_p; b.proj = s->d_proj;
         b.gprior = s->d_gprior; b.lossf = s->d_lossf; b.gaa = grad_aa; b.gtran = grad_tran; b.T = T;
-        RC_LAUNCH(rc_smplify_bwd_kernel, rc_cdiv(T, 32), 32, 0, stream, s->model->d_const, b);
+        RC_LAUNCH(rc_smplify_bwd_kernel, rc_cdiv(T, kSmpWarps), kSmpWarps * 32, 0, stream, s->model->d_const, b);
         RC_CHECK_LAUNCH();
     }
     if (loss) {
@@ -779,8 +820,12 @@ int rc_smplify_run(rc_smplify* s, int32_t n_seq, const float* aa_init, const flo
     a.aa_out = aa_out; a.tran_out = tran_out; a.stats = stats; a.C = s->d_const; a.Psym = s->d_psym;
     a.T = T; a.n = (int)n; a.max_iter = max_iter; a.max_eval = max_iter * 5 / 4; a.hist = s->run_hist; a.camk_stride = camk_per_seq ? 9 : 0;
     a.lr = lr;
-    const int threads = std::min(kLbThreadsMax, std::max(256, (T + 31) / 32 * 32));
-    RC_LAUNCH(rc_smplify_lbfgs_kernel, n_seq, threads, 0, stream, s->model->d_const, a);
+    // one warp per frame inside the block: 16 warps walk the frames of the sequence
+    const int threads = kLbThreadsMax;
+    const size_t smem = ((sizeof(LbShared) + 15) / 16) * 16 + (size_t)(threads / 32) * sizeof(SmpWarp);
+    static bool attr = false;
+    if (!attr) { RC_CUDA(cudaFuncSetAttribute(rc_smplify_lbfgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    RC_LAUNCH(rc_smplify_lbfgs_kernel, n_seq, threads, smem, stream, s->model->d_const, a);
     RC_CHECK_LAUNCH();
     return RC_OK;
 }
