@@ -604,6 +604,27 @@ int grouped_tail(rc_state* s, bool advance, void* stream) {
     return RC_OK;
 }
 
+// ---- time-chunked host transfers (rc_forward_sequence_host) ------------------------------------------------------------------------
+int chunk_before(rc_state* s, int t, cudaStream_t st) {
+    const rc_state::ChunkIO& c = s->cio;
+    if (!c.chunk || t % c.chunk) return RC_OK;
+    RC_CUDA(cudaStreamWaitEvent(st, c.ev_in[t / c.chunk], 0));          // the chunk's inputs have landed
+    return RC_OK;
+}
+int chunk_after(rc_state* s, int t, cudaStream_t st) {
+    const rc_state::ChunkIO& c = s->cio;
+    if (!c.chunk || ((t + 1) % c.chunk && t + 1 != c.T)) return RC_OK;
+    const int k = t / c.chunk, t0 = k * c.chunk, n = t + 1 - t0;
+    const size_t B = (size_t)s->B, T = (size_t)c.T;
+    RC_CUDA(cudaEventRecord(c.ev_out[k], st));
+    RC_CUDA(cudaStreamWaitEvent(c.d2h, c.ev_out[k], 0));
+    RC_CUDA(cudaMemcpy2DAsync(c.hp + (size_t)t0 * 216, T * 216 * sizeof(float), s->hp + (size_t)t0 * 216, T * 216 * sizeof(float),
+                              (size_t)n * 216 * sizeof(float), B, cudaMemcpyDeviceToHost, c.d2h));
+    RC_CUDA(cudaMemcpy2DAsync(c.ht + (size_t)t0 * 3, T * 3 * sizeof(float), s->ht + (size_t)t0 * 3, T * 3 * sizeof(float),
+                              (size_t)n * 3 * sizeof(float), B, cudaMemcpyDeviceToHost, c.d2h));
+    return RC_OK;
+}
+
 bool grouped_path(const rc_state* s) { return s->net->gemm_mode >= 2 && s->ph_ready && s->B > 8; }
 
 int enqueue_step(rc_state* s, const StepIO& io, int any_first_frame, bool advance, void* stream) {
@@ -891,6 +912,10 @@ void rc_state_destroy(rc_state* s) {
     for (void* p : s->allocs) cudaFree(p);
     cudaFree(s->hj); cudaFree(s->ha); cudaFree(s->ho); cudaFree(s->hp); cudaFree(s->ht); cudaFree(s->hft);
     cudaFree(s->hlen); cudaFree(s->hfl);
+    if (s->cio.h2d) cudaStreamDestroy(s->cio.h2d);
+    if (s->cio.d2h) cudaStreamDestroy(s->cio.d2h);
+    for (cudaEvent_t e : s->cio.ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : s->cio.ev_out) cudaEventDestroy(e);
     delete s;
 }
 
@@ -1021,7 +1046,9 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
     io.branch = s->branch_log; io.sb = T;
     // (Tried: rotating the loop so that init_net of frame t overlaps prep + lists of frame t + 1 — its four launches take ~37 us on the
     // side stream even when the list is empty, longer than prep + lists, so nothing was gained: 525 vs 527 us per frame.)
+    RC_TRY(chunk_before(s, 0, st));
     RC_TRY(enqueue_step(s, io, any_first_frame, true, stream));
+    RC_TRY(chunk_after(s, 0, st));
     if (T == 1) return RC_OK;
     if (s->B == 1 && !lengths && rc_stream2_supported(s) && !rc_stream_supported(s)) {
         // a single stream: one TMA-staged cooperative kernel per frame (stream2.cu)
@@ -1045,7 +1072,11 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
         return rc_seq_run(s, io, T, t0, bn, stream);
     }
     if (!use_graph) {
-        for (int t = 1; t < T; ++t) RC_TRY(enqueue_step(s, io, 0, true, stream));
+        for (int t = 1; t < T; ++t) {
+            RC_TRY(chunk_before(s, t, st));
+            RC_TRY(enqueue_step(s, io, 0, true, stream));
+            RC_TRY(chunk_after(s, t, st));
+        }
         g_tl.report(11);
         return RC_OK;
     }
@@ -1069,7 +1100,11 @@ int rc_forward_sequence(rc_state* s, int32_t T, const float* j2dc, const float* 
         if (e != cudaSuccess) { s->graph = nullptr; rc_set_error("graph instantiate: %s", cudaGetErrorString(e)); return RC_ERR_CUDA; }
         s->graph_key = key;
     }
-    for (int t = 1; t < T; ++t) RC_CUDA(cudaGraphLaunch(s->graph, st));
+    for (int t = 1; t < T; ++t) {
+        RC_TRY(chunk_before(s, t, st));
+        RC_CUDA(cudaGraphLaunch(s->graph, st));
+        RC_TRY(chunk_after(s, t, st));
+    }
     g_rc_launches.fetch_add(s->graph_nodes * (long long)(T - 1));
     return RC_OK;
 }
@@ -1095,9 +1130,14 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* hj, const floa
         if (!s->hfl) RC_CUDA(cudaMalloc(&s->hfl, B * sizeof(int)));
         s->host_cap_T = T;
     }
-    RC_CUDA(cudaMemcpyAsync(s->hj, hj, B * T * 99 * sizeof(float), cudaMemcpyHostToDevice, st));
-    RC_CUDA(cudaMemcpyAsync(s->ha, ha, B * T * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
-    RC_CUDA(cudaMemcpyAsync(s->ho, ho, B * T * 54 * sizeof(float), cudaMemcpyHostToDevice, st));
+    // Multi-launch path (more than 128 streams): the frames are launched one by one, so the transfers are cut into chunks of frames —
+    // inputs of chunk k + 1 upload and results of chunk k - 1 download while chunk k computes (two copy streams, strided 2-D copies
+    // of the [B, T, ...] slabs).  The one-launch paths (sequence kernel, single stream) copy everything before / after.
+    static const int chunk_env = getenv("RC_HOST_CHUNK") ? atoi(getenv("RC_HOST_CHUNK")) : 30;
+    const bool want_seq = s->net->gemm_mode == 3 || (s->net->gemm_mode == 2 && s->B <= s->net->seq_auto_B && T >= 3 * s->net->seq_warm);
+    const bool chunked = chunk_env > 0 && grouped_path(s) && !(want_seq && rc_seq_supported(s)) && T > chunk_env;
+    rc_state::ChunkIO& c = s->cio;
+    c.chunk = 0;
     if (hft) RC_CUDA(cudaMemcpyAsync(s->hft, hft, B * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
     if (hlen) RC_CUDA(cudaMemcpyAsync(s->hlen, hlen, B * sizeof(int), cudaMemcpyHostToDevice, st));
     int any_ff = 0;
@@ -1109,10 +1149,45 @@ int rc_forward_sequence_host(rc_state* s, int32_t T, const float* hj, const floa
         RC_CUDA(cudaMemsetAsync(s->hp, 0, B * T * 216 * sizeof(float), st));
         RC_CUDA(cudaMemsetAsync(s->ht, 0, B * T * 3 * sizeof(float), st));
     }
-    RC_TRY(rc_forward_sequence(s, T, s->hj, s->ha, s->ho, hlen ? s->hlen : nullptr, nullptr, hft ? s->hft : nullptr,
-                               hfl ? s->hfl : nullptr, any_ff, s->hp, s->ht, use_graph, stream));
-    RC_CUDA(cudaMemcpyAsync(hp, s->hp, B * T * 216 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    RC_CUDA(cudaMemcpyAsync(ht, s->ht, B * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (chunked) {
+        if (!c.h2d) {
+            RC_CUDA(cudaStreamCreateWithFlags(&c.h2d, cudaStreamNonBlocking));
+            RC_CUDA(cudaStreamCreateWithFlags(&c.d2h, cudaStreamNonBlocking));
+        }
+        const int nchunk = (T + chunk_env - 1) / chunk_env;
+        while ((int)c.ev_in.size() < nchunk) {
+            cudaEvent_t a, b2;
+            RC_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            RC_CUDA(cudaEventCreateWithFlags(&b2, cudaEventDisableTiming));
+            c.ev_in.push_back(a); c.ev_out.push_back(b2);
+        }
+        // the copy streams start after what is already queued on the caller's stream (buffer reuse by a previous call)
+        RC_CUDA(cudaEventRecord(c.ev_out[0], st));
+        RC_CUDA(cudaStreamWaitEvent(c.h2d, c.ev_out[0], 0));
+        RC_CUDA(cudaStreamWaitEvent(c.d2h, c.ev_out[0], 0));
+        for (int k = 0; k < nchunk; ++k) {
+            const size_t t0 = (size_t)k * chunk_env, n = std::min<size_t>(chunk_env, T - t0);
+            RC_CUDA(cudaMemcpy2DAsync(s->hj + t0 * 99, (size_t)T * 99 * 4, hj + t0 * 99, (size_t)T * 99 * 4, n * 99 * 4, B, cudaMemcpyHostToDevice, c.h2d));
+            RC_CUDA(cudaMemcpy2DAsync(s->ha + t0 * 18, (size_t)T * 18 * 4, ha + t0 * 18, (size_t)T * 18 * 4, n * 18 * 4, B, cudaMemcpyHostToDevice, c.h2d));
+            RC_CUDA(cudaMemcpy2DAsync(s->ho + t0 * 54, (size_t)T * 54 * 4, ho + t0 * 54, (size_t)T * 54 * 4, n * 54 * 4, B, cudaMemcpyHostToDevice, c.h2d));
+            RC_CUDA(cudaEventRecord(c.ev_in[k], c.h2d));
+        }
+        c.chunk = chunk_env; c.T = T; c.hp = hp; c.ht = ht;
+    } else {
+        RC_CUDA(cudaMemcpyAsync(s->hj, hj, B * T * 99 * sizeof(float), cudaMemcpyHostToDevice, st));
+        RC_CUDA(cudaMemcpyAsync(s->ha, ha, B * T * 18 * sizeof(float), cudaMemcpyHostToDevice, st));
+        RC_CUDA(cudaMemcpyAsync(s->ho, ho, B * T * 54 * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    const int rc = rc_forward_sequence(s, T, s->hj, s->ha, s->ho, hlen ? s->hlen : nullptr, nullptr, hft ? s->hft : nullptr,
+                                       hfl ? s->hfl : nullptr, any_ff, s->hp, s->ht, use_graph, stream);
+    c.chunk = 0;
+    if (rc != RC_OK) return rc;
+    if (chunked) {
+        RC_CUDA(cudaStreamSynchronize(c.d2h));
+    } else {
+        RC_CUDA(cudaMemcpyAsync(hp, s->hp, B * T * 216 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        RC_CUDA(cudaMemcpyAsync(ht, s->ht, B * T * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     RC_CUDA(cudaStreamSynchronize(st));
     return RC_OK;
 }

@@ -127,6 +127,14 @@ struct rc_state {
     unsigned* sk_bar = nullptr;
     int* sk_rows = nullptr;            // [0] = row 0, [1] = count 1, [4..5] = frame flags / need_init
     int* flags_sk = nullptr;
+    // rc_forward_sequence_host with time-chunked transfers (multi-launch path): the frame loop waits for the chunk's inputs and
+    // signals finished chunks, the copies run on two extra streams
+    struct ChunkIO {
+        int chunk = 0, T = 0;                        // frames per chunk (0 = off)
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        std::vector<cudaEvent_t> ev_in, ev_out;
+        float *hp = nullptr, *ht = nullptr;          // host destinations
+    } cio;
     // staging buffers of rc_forward_sequence_host
     float *hj = nullptr, *ha = nullptr, *ho = nullptr, *hp = nullptr, *ht = nullptr, *hft = nullptr;
     int *hlen = nullptr, *hfl = nullptr;

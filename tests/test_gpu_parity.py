@@ -472,3 +472,21 @@ def test_sequence_kernel_matches_grouped(rb, body, B, conf, ragged):
     finally:
         net.set_gemm_mode(2)
         net.set_seq_options(auto_max_streams=128, warm_frames=16)
+
+
+@pytest.mark.parametrize('ragged', [False, True])
+def test_host_entry_chunked_transfers(rb, body, ragged):
+    """rc_forward_sequence_host on the multi-launch path (> 128 streams) uploads / downloads in chunks of 30 frames on two copy
+    streams while the frames compute; the result must equal the device-resident call bit for bit (also the zeros of ragged rows)."""
+    net = get_net(rb, body, 0, 'contact')
+    B, T = 160, 75
+    inp = synthetic.make_inputs(B, T, seed=12, conf='mixed')
+    rb.Net.gravityc = inp['gravity'].clone()
+    lengths = (torch.arange(B) * 7 % (T - 20) + 20).to(torch.int32) if ragged else None
+    ft = torch.tensor([0., 0., 4.])
+    pd, td = net.forward_offline(inp['j2dc'].cuda(), inp['accc'].cuda(), inp['oric'].cuda(), first_tran=ft, lengths=lengths)
+    pin = lambda x: x.contiguous().pin_memory()
+    hp, ht = torch.full((B, T, 24, 3, 3), 7.).pin_memory(), torch.full((B, T, 3), 7.).pin_memory()
+    for _ in range(2):                       # second call: buffers and events are reused
+        net.forward_offline(pin(inp['j2dc']), pin(inp['accc']), pin(inp['oric']), first_tran=ft, lengths=lengths, out=(hp, ht))
+        assert torch.equal(hp, pd.cpu()) and torch.equal(ht, td.cpu())
