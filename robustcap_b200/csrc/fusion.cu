@@ -994,10 +994,15 @@ int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const f
     io.j2dc = s->on_din; io.accc = s->on_din + 99; io.oric = s->on_din + 117; io.sj = 99; io.sa = 18; io.so = 54;
     io.gravity = nullptr; io.first_tran = s->on_din + 171; io.row_flags = (const int*)(s->on_din + 174); io.lengths = nullptr;
     io.pose = s->on_dout; io.tran = s->on_dout + 216; io.sp = 216; io.st = 3; io.d_t = nullptr; io.first_mode = 1;
+    bool direct_out = false;
     if (rc_stream_supported(s)) {
         RC_TRY(rc_stream_frame(s, io, first_frame, stream));    // the whole frame as one cooperative kernel (stream.cu)
     } else if (!first_frame && rc_stream2_supported(s)) {
-        RC_TRY(rc_stream2_frame(s, io, 0, stream));             // one cooperative kernel, weights TMA-staged through shared memory (stream2.cu)
+        // one kernel, weights TMA-staged through shared memory (stream2.cu); kin writes pose / tran straight into the pinned host
+        // buffer (unified addressing), which saves the device-to-host copy on the latency path
+        io.pose = s->on_hout; io.tran = s->on_hout + 216;
+        direct_out = true;
+        RC_TRY(rc_stream2_frame(s, io, 0, stream));
     } else if (first_frame) {
         RC_TRY(enqueue_step(s, io, 1, false, stream));          // extra rnn6 pass (sig_mp.py:155-156): direct launches
     } else {
@@ -1022,7 +1027,7 @@ int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const f
         RC_CUDA(cudaGraphLaunch(s->on_graph, st));
         g_rc_launches.fetch_add(s->on_graph_nodes);
     }
-    RC_CUDA(cudaMemcpyAsync(s->on_hout, s->on_dout, kOnOut * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (!direct_out) RC_CUDA(cudaMemcpyAsync(s->on_hout, s->on_dout, kOnOut * sizeof(float), cudaMemcpyDeviceToHost, st));
     RC_CUDA(cudaStreamSynchronize(st));
     memcpy(h_pose, s->on_hout, 216 * sizeof(float));
     memcpy(h_tran, s->on_hout + 216, 3 * sizeof(float));

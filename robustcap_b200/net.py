@@ -62,7 +62,10 @@ class Net(torch.nn.Module):
         self._net = None            # rc_net handle
         self._states = {}           # batch size -> rc_state handle
         self._cfg_pushed = None
+        self._cfg_raw = None
         self._grav_pushed = {}
+        self._grav_seen = {}
+        self._grav_keep = {}
         self._dirty = True
         self._use_graph = True
         self._fp = None
@@ -91,6 +94,8 @@ class Net(torch.nn.Module):
             lib.rc_state_destroy(h)
         self._states = {}
         self._grav_pushed = {}
+        self._grav_seen = {}
+        self._grav_keep = {}
         if self._net is not None:
             lib.rc_net_destroy(self._net)
             self._net = None
@@ -115,11 +120,17 @@ class Net(torch.nn.Module):
         if check_params and not self._dirty and self._fingerprint() != self._fp:
             self._dirty = True
         if self._net is not None and not self._dirty:
-            cfg = self._config()
-            key = bytes(cfg)
-            if key != self._cfg_pushed:
-                _lib.check(lib.rc_net_set_config(self._net, ctypes.byref(cfg)))
-                self._cfg_pushed = key
+            # the class-level knobs may be changed at any time (evaluate.py:254, 337, 392): compare the raw attribute values (cheap, this
+            # runs on every streaming frame) and push a new config only when one moved
+            raw = (self.conf_range, self.tran_filter_num, self.contact_threshold, self.height_threhold, self.distrance_threshold,
+                   self.use_flat_floor, self.live, self.update_vision_freq)
+            if raw != self._cfg_raw:
+                cfg = self._config()
+                key = bytes(cfg)
+                if key != self._cfg_pushed:
+                    _lib.check(lib.rc_net_set_config(self._net, ctypes.byref(cfg)))
+                    self._cfg_pushed = key
+                self._cfg_raw = raw
             return
         self._release()
         cfg = self._config()
@@ -140,11 +151,16 @@ class Net(torch.nn.Module):
             h = _lib.vp()
             _lib.check(lib.rc_state_create(ctypes.byref(h), self._net, B))
             self._states[B] = h
-        g = self.gravityc.detach().to('cpu', torch.float32).reshape(3).contiguous()
-        key = tuple(g.tolist())
-        if self._grav_pushed.get(B) != key:
-            _lib.check(lib.rc_state_set_gravity(self._states[B], _lib.hptr(g), _lib.stream()))
-            self._grav_pushed[B] = key
+        gc = self.gravityc                                  # callers overwrite it per sequence (evaluate.py:73, 180, 285, 337)
+        seen = (id(gc), gc._version)
+        if self._grav_seen.get(B) != seen:                  # same tensor object, not modified in place: nothing to do (per-frame path)
+            g = gc.detach().to('cpu', torch.float32).reshape(3).contiguous()
+            key = tuple(g.tolist())
+            if self._grav_pushed.get(B) != key:
+                _lib.check(lib.rc_state_set_gravity(self._states[B], _lib.hptr(g), _lib.stream()))
+                self._grav_pushed[B] = key
+            self._grav_seen[B] = seen
+            self._grav_keep[B] = gc                         # keeps id() unique while cached
         return self._states[B]
 
     def load_state_dict(self, *args, **kwargs):
