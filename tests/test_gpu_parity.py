@@ -193,7 +193,31 @@ def test_forward_offline_batched_golden(rb, body, golden_dir, variant, gemm_mode
     net.set_gemm_mode(2)
 
 
-def test_tensor_core_gemm_matches_simt(rb, body):
+def worst_rows_vs_float64(assets, inp, kw_of_row, results, rows, T):
+    """The committed measurement behind the back-end comparisons: for the streams where two back ends differ most, every back end's
+    geodesic error against the float64 oracle next to the float32 oracle's own error against float64 (per-joint counts above the
+    1e-4 rad bar, maxima).  `results`: {name: pose [B, T, 24, 3, 3] cpu}.  Asserts that no back end is further from float64 than the
+    bar or twice the reference arithmetic's own error, whichever is larger."""
+    from oracle.kinematics import BodyOracle
+    from oracle.fusion import FusionOracle
+    sd = get_sd(0, 'contact')
+    o32 = FusionOracle(sd, BodyOracle(assets['smpl_file']))
+    o64 = FusionOracle(sd, BodyOracle(assets['smpl_file'], dtype=torch.float64), dtype=torch.float64)
+    for b in rows:
+        kw = kw_of_row(b)
+        n = T if 'length' not in kw else kw.pop('length')
+        p32, _ = o32.run(inp['j2dc'][b, :n], inp['accc'][b, :n], inp['oric'][b, :n], gravity=inp['gravity'], **kw)
+        p64, _ = o64.run(inp['j2dc'][b, :n], inp['accc'][b, :n], inp['oric'][b, :n], gravity=inp['gravity'], **kw)
+        e_ref = pose_angle(p32.double(), p64)
+        line = 'stream %4d: oracle32 vs float64 max %.2e rad (%d joints > 1e-4)' % (b, e_ref.max().item(), int((e_ref > RAD_TOL).sum()))
+        for name, pose in results.items():
+            e = pose_angle(pose[b, :n].double(), p64)
+            line += ' | %s max %.2e (%d > 1e-4)' % (name, e.max().item(), int((e > RAD_TOL).sum()))
+            assert bool((e <= torch.clamp(2 * e_ref, min=RAD_TOL) + 2e-5).all()), (name, b, e.max().item(), e_ref.max().item())
+        print(line)
+
+
+def test_tensor_core_gemm_matches_simt(rb, body, assets):
     """The split-fp16 tcgen05 GEMMs (per-layer kernel, mode 1; persistent grouped kernel, mode 2) against the fp32 SIMT GEMM on
     the same batch: 200 sequences (ragged M tile), 10 frames.  All are fp32-accurate evaluations of the same dot products, so
     they agree to reduction-order noise."""
@@ -205,6 +229,7 @@ def test_tensor_core_gemm_matches_simt(rb, body):
     net.set_gemm_mode(0)
     p0, t0 = net.forward_offline(j, a, o, first_tran=ft)
     d0 = {k: v.clone() for k, v in net.debug_outputs(200).items()}
+    res, worst = {'simt': p0.cpu()}, set()
     for mode in (1, 2):
         net.set_gemm_mode(mode)
         p1, t1 = net.forward_offline(j, a, o, first_tran=ft)
@@ -216,13 +241,17 @@ def test_tensor_core_gemm_matches_simt(rb, body):
         terr = (t0 - t1).abs().max().item()
         print('mode %d: pose max %.2e rad, 99.9 %% %.2e rad, tran %.2e m' % (mode, ang.max().item(), ang.quantile(0.999).item(), terr))
         # two float32-accurate evaluations differ by reduction order only; the rare ill-conditioned joints (tiny 6D vectors through
-        # Gram-Schmidt with random-init weights) amplify that noise, hence a quantile bound plus a loose cap on the maximum
-        assert ang.quantile(0.999).item() < 5e-5 and ang.max().item() < 5e-4 and terr < 1e-4, mode
+        # Gram-Schmidt with random-init weights) amplify that noise: quantile bound here, and for the worst streams the error of
+        # every back end against the float64 oracle next to the float32 oracle's own (below)
+        assert ang.quantile(0.999).item() < 5e-5 and terr < 1e-4, mode
+        res['mode%d' % mode] = p1.cpu()
+        worst.update(ang.view(200, -1).amax(dim=1).topk(3).indices.tolist())
     net.set_gemm_mode(2)
+    worst_rows_vs_float64(assets, inp, lambda b: {'first_tran': torch.tensor([0., 0., 4.])}, res, sorted(worst), 10)
 
 
 @pytest.mark.parametrize('B', [130, 300])
-def test_grouped_kernel_odd_row_blocks(rb, body, B):
+def test_grouped_kernel_odd_row_blocks(rb, body, assets, B):
     """Persistent grouped kernel on CTA pairs with an odd number of 128-row blocks (the peer CTA of the last pair has no rows, or a
     partial block), ragged lengths and mixed start modes, against the fp32 SIMT back end on the same batch."""
     net = get_net(rb, body, 0, 'contact')
@@ -240,9 +269,18 @@ def test_grouped_kernel_odd_row_blocks(rb, body, B):
         p2, t2 = net.forward_offline(j, a, o, use_graph=use_graph, **kw)
         valid = (torch.arange(T)[None, :] < lengths[:, None])                       # frames beyond a length are zero in both
         ang = pose_angle(p0.cpu()[valid], p2.cpu()[valid])
-        assert ang.quantile(0.999).item() < 5e-5 and ang.max().item() < 5e-4, (B, use_graph, ang.max().item())
+        assert ang.quantile(0.999).item() < 5e-5, (B, use_graph, ang.max().item())
         assert (t0 - t2).abs().max().item() < 1e-4
         assert p2.cpu()[~valid].abs().max().item() == 0 and torch.equal(p0.cpu()[~valid], p2.cpu()[~valid])
+    # the streams where the two back ends differ most, each against the float64 oracle (and the float32 oracle's own error)
+    full = pose_angle(p0.cpu(), p2.cpu()).view(B, T, 24)
+    full[~valid] = 0
+    rows = full.view(B, -1).amax(dim=1).topk(3).indices.tolist()
+    def kw_of_row(b):
+        d = {'first_frame': True} if ff[b] else {'first_tran': torch.tensor([0., 0., 4.])}
+        d['length'] = int(lengths[b])
+        return d
+    worst_rows_vs_float64(assets, inp, kw_of_row, {'simt': p0.cpu(), 'grouped': p2.cpu()}, sorted(rows), T)
 
 
 def test_offline_vs_oracle_seeded(rb, body, assets):
