@@ -39,7 +39,7 @@ class ParametricModel:
         if self._handle is None:
             lib = _lib.load()
             _lib.require_cuda()
-            j, v = self.get_zero_pose_joint_and_vertex()
+            j, v = getattr(self, '_shaped_jv', None) or self.get_zero_pose_joint_and_vertex()
             j = j.detach().cpu().float().contiguous()
             v = v.detach().cpu().float().contiguous()
             w = self._skinning_weights.detach().cpu().float().contiguous()
@@ -50,6 +50,18 @@ class ParametricModel:
                                            _lib.hptr(par), _lib.hptr(mp)))
             self._handle = h
         return self._handle
+
+    def shaped(self, shape: torch.Tensor):
+        r"""A view of this body with the rest pose of ``shape`` ([10] betas) baked into the native constants — what
+        ``forward_kinematics(..., shape=shape)`` uses in the reference (model.py:78-93, 224-241) — for the native paths that take a
+        body handle (SMPLify with ``shape=``, temporal_smplify.py:84-86, 158-159).  Shares all tensors with ``self``."""
+        import copy
+        other = copy.copy(self)
+        other._handle = None
+        other._dev_consts = None
+        j, v = self.get_zero_pose_joint_and_vertex(shape.detach().reshape(1, 10).to(self._v_template.device, torch.float32))
+        other._shaped_jv = (j.reshape(24, 3), v.reshape(-1, 3))
+        return other
 
     def __del__(self):
         try:

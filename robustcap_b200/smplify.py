@@ -54,7 +54,6 @@ class TemporalSMPLify:
     def __init__(self, cam_k, imu_ori, step_size=1.0, num_iters=1, use_lbfgs=True, device=None, batch_size=1, max_iter=20,
                  shape=None, use_head=False, body_model=None):
         assert use_lbfgs, 'the Adam branch of the reference (temporal_smplify.py:167-180) is broken upstream and not provided'
-        assert shape is None, 'shaped bodies are not supported by the native SMPLify objective yet'
         self.device = _lib.require_cuda()
         self.step_size, self.max_iter, self.num_iters, self.batch_size = step_size, max_iter, num_iters, batch_size
         self.cam_k = cam_k.detach().clone().to(self.device, torch.float32).contiguous()
@@ -65,7 +64,8 @@ class TemporalSMPLify:
             if TemporalSMPLify.body_model is None:
                 TemporalSMPLify.body_model = ParametricModel(TemporalSMPLify.smpl_file)
             body_model = TemporalSMPLify.body_model
-        self.body = body_model
+        # temporal_smplify.py:84-86, 158-159: an optional [10] shape vector changes the rest pose the closure skins
+        self.body = body_model if shape is None else body_model.shaped(torch.as_tensor(shape))
         lib = _lib.load()
         h = _lib.vp()
         _lib.check(lib.rc_smplify_create(ctypes.byref(h), self.body._native(), _lib.hptr(self.pose_prior.means.contiguous()),

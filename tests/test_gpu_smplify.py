@@ -136,3 +136,29 @@ def test_batched_sequences(env, golden_dir):
         p1, t1, _ = smplify.smplify_runner(pose[s_], tran[s_], kp[s_].clone(), ori[s_], batch_size=T, lr=1e-3, cam_k=g['cam_k'],
                                            loss_threshold=1e12, max_iter=5)
         assert torch.equal(p1, bp[s_].cpu()) and torch.equal(t1, bt[s_].cpu())
+
+
+def test_shaped_body(env, golden_dir):
+    """``smplify_runner(..., shape=betas)`` (run.py:21, temporal_smplify.py:84-86, 158-159): the closure skins the SHAPED rest pose.
+    The native constants of ``ParametricModel.shaped(betas)`` must give the same 33 points as the full shaped mesh path (golden-pinned
+    in test_smpl_forward_kinematics), and the runner must reduce its objective on the shaped body."""
+    rb, smplify, body = env
+    from robustcap_b200.net import sync_mp3d
+    g = load(golden_dir, 'smplify_it5.npz')
+    k = load(golden_dir, 'kinematics.npz')
+    shape = k['shape'][0]
+    T = g['pose_in'].shape[0]
+    sb = body.shaped(shape)
+    _, kp = sb.keypoints33(g['pose_in'].cuda(), g['tran_in'].cuda())
+    _, gj, gv = body.forward_kinematics(g['pose_in'].cuda(), shape=shape.cuda().expand(T, 10), tran=g['tran_in'].cuda(), calc_mesh=True)
+    for t in (0, T - 1):
+        assert (kp[t] - sync_mp3d(gv[t], gj[t])).abs().max().item() < 5e-6
+    _, kp_mean = body.keypoints33(g['pose_in'].cuda(), g['tran_in'].cuda())
+    assert (kp - kp_mean).abs().max().item() > 1e-3                        # the shape really moves the points
+    sm = smplify.TemporalSMPLify(cam_k=g['cam_k'], imu_ori=g['imu_ori'], step_size=1e-3, batch_size=T, max_iter=5, shape=shape)
+    pose, tran, rl = sm(g['pose_in'], g['tran_in'], g['j2d_pix'].clone())
+    st = sm.last_stats.cpu()
+    assert st[0, 1] < st[0, 0] and torch.isfinite(pose).all()
+    pose2, tran2, upd = smplify.smplify_runner(g['pose_in'], g['tran_in'], g['j2d_pix'].clone(), g['imu_ori'], batch_size=T, lr=1e-3,
+                                               cam_k=g['cam_k'], loss_threshold=1e12, shape=shape, max_iter=5)
+    assert torch.equal(pose2.reshape(-1), pose.reshape(-1).cpu())
