@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
         return SO_PATH
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     tmp = '%s.%d.tmp' % (SO_PATH, os.getpid())        # several ranks may build at once: private temp file + atomic rename
-    cmd = [nvcc] + NVCC_FLAGS + ['-o', tmp] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get('RC_NVCC_EXTRA', '').split() + ['-o', tmp] + sources()   # RC_NVCC_EXTRA: -D switches of timing experiments
     if verbose:
         print(' '.join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)

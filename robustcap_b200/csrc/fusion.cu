@@ -406,11 +406,13 @@ int build_phase(rc_state* s, int ph, const ChainSpec* ch, int nch) {
             if (idx[c][layer] < 0) continue;
             RcPhJob& j = d->job[idx[c][layer]];
             j.rows = rows; j.count = count; j.H = H;
+            j.level = layer;
             j.dep = layer ? idx[c][layer - 1] : -1;
             if (layer == 0) {
                 mk(&j.mAhi, Ph[0], w.K1p); mk(&j.mAlo, Pl[0], w.K1p);
                 j.mWhi = w.mW1hi; j.mWlo = w.mW1lo; j.mWhi64 = w.mW1hi64; j.mWlo64 = w.mW1lo64; j.bias = w.b1; j.N = H; j.relu = 1; j.K = w.K1p;
                 j.nAhi = Ph[1]; j.nAlo = Pl[1]; j.npitch = 2 * H; j.kind = 0; j.nt = H / RC_TC_BN;
+                j.nt2 = (H + 255) / 256; j.nmma = H >= 256 ? 256 : (H + 15) / 16 * 16;
             } else if (layer == 1 || layer == 2) {
                 const int l = layer - 1;
                 mk(&j.mAhi, Ph[layer], 2 * H); mk(&j.mAlo, Pl[layer], 2 * H);
@@ -418,10 +420,12 @@ int build_phase(rc_state* s, int ph, const ChainSpec* ch, int nch) {
                 if (l == 0) { j.nAhi = Ph[2]; j.nAlo = Pl[2]; j.npitch = 2 * H; }
                 else if (ch[c].Y) { j.nAhi = Ph[3]; j.nAlo = Pl[3]; j.npitch = H; }
                 j.kind = 1; j.nt = 4 * H / RC_TC_BN;
+                j.nt2 = 4 * H / 256; j.nmma = 256;
             } else {
                 mk(&j.mAhi, Ph[3], H); mk(&j.mAlo, Pl[3], H);
                 j.mWhi = w.mW2hi; j.mWlo = w.mW2lo; j.mWhi64 = w.mW2hi64; j.mWlo64 = w.mW2lo64; j.bias = w.b2; j.Y = ch[c].Y; j.ldy = ch[c].ldy; j.N = w.out; j.K = H;
                 j.kind = 0; j.nt = w.outp / RC_TC_BN;
+                j.nt2 = (w.out + 255) / 256; j.nmma = w.out >= 256 ? 256 : (w.out + 15) / 16 * 16;
             }
             max_tiles += MT * j.nt;
         }
@@ -536,7 +540,7 @@ int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr) {
         }
         RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     }
-    RC_TRY(rc_tc_phase(s->d_phase[ph], s->d_ctl[ph], s->ph_MT, s->ph_max_tiles[ph], stream, s->d_trace[ph]));
+    RC_TRY(rc_tc_phase(s->d_phase[ph], s->d_ctl[ph], s->ph_MT, s->ph_max_tiles[ph], stream, s->d_trace[ph], ph == PH_LATE || ph == PH_6A ? 128 : 256));
     if (s->prof_on) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     g_tl.mark(ph == PH_1 ? "phase1" : ph == PH_2 ? "phase2" : ph == PH_LATE ? "phaseL" : "phase6a", stream);
     return RC_OK;

@@ -56,6 +56,12 @@ for ph in (0, 2, 3):
         s2 = job == jj
         print('   job %2d MMA thread waits (median cycles): tile descriptor %6d | accumulators handed back %6d | operand stages (sum over K blocks) %6d of %6d issue time' % (
             jj, np.median(tr[s2, 9]), np.median(tr[s2, 10]), np.median(tr[s2, 11]), np.median(mma[s2])))
+    if os.environ.get('RC_PH_PAIR', '0') == '2':      # 256 x 256 pair kernel: epilogue breakdown (slots 5, 12, 8, 13, 14, 15, 6)
+        for jj in np.unique(job):
+            s2 = job == jj
+            g = lambda a, b: int(np.median(tr[s2, a] - tr[s2, b]))
+            print('   job %2d epilogue (median cycles): corr drain %6d | wait + main drain %6d | cprev load %6d | gate math %6d | C / H stores %6d | split stores %6d' % (
+                jj, g(12, 5), g(8, 12), g(13, 8), g(14, 13), g(15, 14), g(6, 15)))
     if len(glob):
         gl = glob[0]
         t_entry, t_grab, t_pub, t_exit = ~int(gl[0]), ~int(gl[1]), int(gl[2]), int(gl[3])
