@@ -514,12 +514,22 @@ struct FrameTimeline {
         std::map<std::string, std::pair<double, int>> acc;
         std::vector<std::string> order;
         for (size_t i = 1; i < used; ++i) {
-            if ((int)i < 2 * slots_per_frame) continue;                 // skip the first two frames
+            static const int skip = getenv("RC_TL_SKIP") ? atoi(getenv("RC_TL_SKIP")) : 2;
+            if ((int)i < skip * slots_per_frame) continue;              // skip the first frames (default two; the init_net re-seeds fall into the first ~16)
             float ms = 0.f;
             cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
             auto& a = acc[tag[i]];
             if (a.second == 0) order.push_back(tag[i]);
             a.first += ms; a.second += 1;
+        }
+        if (getenv("RC_TL_FRAMES")) {                                    // frame-by-frame totals (us), ten per line
+            fprintf(stderr, "[frame totals, us]");
+            for (size_t f = 0; (f + 1) * slots_per_frame < used; ++f) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[f * slots_per_frame], ev[(f + 1) * slots_per_frame]);
+                fprintf(stderr, "%s%.0f", f % 10 ? " " : "\n  ", 1e3 * ms);
+            }
+            fprintf(stderr, "\n");
         }
         double tot = 0;
         for (auto& k : order) tot += acc[k].first / acc[k].second;
@@ -540,7 +550,11 @@ int run_phase(rc_state* s, int ph, void* stream, int* advance = nullptr) {
         }
         RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     }
-    RC_TRY(rc_tc_phase(s->d_phase[ph], s->d_ctl[ph], s->ph_MT, s->ph_max_tiles[ph], stream, s->d_trace[ph], ph == PH_LATE || ph == PH_6A ? 128 : 256));
+    // (Measured: in a steady frame the init_net launches of the side stream are empty and the join costs 2.6 us; leaving SMs free for
+    // them during the updater phase, RC_LATE_RESERVE, does not pay.)
+    static const int late_reserve = getenv("RC_LATE_RESERVE") ? atoi(getenv("RC_LATE_RESERVE")) : 0;
+    RC_TRY(rc_tc_phase(s->d_phase[ph], s->d_ctl[ph], s->ph_MT, s->ph_max_tiles[ph], stream, s->d_trace[ph], ph == PH_LATE || ph == PH_6A ? 128 : 256,
+                       ph == PH_LATE ? late_reserve : 0));
     if (s->prof_on) RC_CUDA(cudaEventRecord(s->prof_ev[s->prof_used++], (cudaStream_t)stream));
     g_tl.mark(ph == PH_1 ? "phase1" : ph == PH_2 ? "phase2" : ph == PH_LATE ? "phaseL" : "phase6a", stream);
     return RC_OK;

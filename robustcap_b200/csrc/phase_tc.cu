@@ -713,30 +713,34 @@ rc_tc_phase_pair_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, i
     }
 }
 
-// ---- CTA-pair version with 256 x 256 tiles (RC_PH_PAIR=2) -------------------------------------------------------------------------
+// ---- CTA-pair version with 256 x 256 tiles (RC_PH_PAIR=2, opt-in) ------------------------------------------------------------------
 // What bounds the two kernels above is the operand traffic INTO an SM per MMA cycle (measured: ~63 B/clk into one SM alone, ~42 B/clk
 // when all 148 stream): a K block of 64 brings 256 (m + n) bytes of split operands for 768 m n / 128^2 MMA cycles, i.e. 85 B/clk for a
 // 128 x 128 tile per CTA and 62 B/clk for the 256 x 128 pair tile.  A pair tile of 256 rows x 256 columns — per CTA its 128 rows of A and
 // its HALF (128 rows) of the W tile — needs 42.7 B/clk and, in shared memory, 40 KB of TMA writes + MMA reads per 384 MMA cycles, so the
-// main loop can run at the tensor pipe's rate.  Price: the accumulators of ONE tile fill the tensor memory (main 256 + corr 256
-// columns), so
+// main loop can run at the tensor pipe's rate (measured: 129 clk per N = 256 MMA of nominally 128).  Price: the accumulators of ONE
+// tile fill the tensor memory (main 256 + corr 256 columns), so
 //   * the two accumulators are handed over separately and the MMA order inside a K block is corr, corr, ..., then main: the epilogue
 //     drains corr while the tile's last main MMAs run, and main while the NEXT tile's first corr MMAs run;
-//   * the truncating accumulate chain of `main` is not split over two alternating buffers but in time: an LSTM tile (K = 2 H) hands
+//   * the truncating accumulate chain of `main` is not split over two alternating buffers but in time: an LSTM tile with K >= 2048 hands
 //     main to the epilogue at half K (the point where its K order switches from the h_prev half to the x half), the epilogue keeps the
-//     partial sums in registers (64 per thread) and the second half starts a fresh chain — same chain lengths as above;
+//     partial sums in registers (64 per thread) and the second half starts a fresh chain — same chain lengths as above (for K = 1024
+//     the hand-over would serialise the epilogue with the second half of the 12 k-clk main loop, so those tiles run one 64-step chain);
 //   * per job the MMA N is the job's width rounded up to 16 (linear2: 16 .. 144 columns instead of a padded 128 / 256);
-//   * a layer level whose 256-column tiles would leave half of the CTA pairs idle (vision updater: one row-block pair) runs 128-column
-//     tiles, decided in the kernel from the row counts;
-//   * the queue hands out the tiles of a layer level row block by row block over all its jobs, so a CTA sees long-K and short-K tiles
-//     mixed: the epilogue of a tile (same length whatever K) hides behind the main loop of the next one on average;
 //   * epilogue: a lane owns one ROW of the tile, so plain stores touch 32 rows x 16 bytes per instruction; everything goes through a
 //     per-warp staging buffer instead, consecutive lanes on consecutive 16-byte pieces of a row, and the previous cell state arrives
-//     in that buffer by cp.async issued when the tile is picked up.
+//     in that buffer by cp.async issued when the tile is picked up; the gate math is branch-free (sigm()) so the units interleave.
+// Template TW = 128 runs 128-column tiles with the same code (32 columns per epilogue thread, 64-row W boxes, corr as two partial sums so
+// that no two consecutive MMAs share an accumulator).  Measured (B = 1024, mixed): a cta_group::2 MMA costs ~123 clk whatever its N
+// (80 .. 256), so narrow tiles halve the work per MMA slot — TW = 128 is slower everywhere and only used for the first-frame rnn6 pass
+// and the vision updater, where 256-column tiles would leave half of the CTA pairs without a tile.
+// Result of the round (profiles/r03_pair256.md): main loop 62-68 k clk per K = 2560 tile (61.4 k ideal), but 288 tiles of up to 68 k clk
+// on 74 pairs pack badly (per-pair span median 210 k, slowest 295 k clk: 4 x 20 tiles per layer for 74 pairs, the second round and the
+// LSTM-1 -> linear2 chain form the tail) and the 64-column epilogue spills (64 accumulators of 96 registers): 576 us per frame against
+// 558 us of the 128 x 128 kernel on the same box.  It stays opt-in; larger batches per GPU (more row blocks) are where it would pay.
 constexpr int kP2Stages = 3;
 constexpr int kP2StageBytes = 2 * kPhABytes + 2 * kPhWBytes;          // 64 KB: A hi / lo (this CTA's 128 rows), W hi / lo (this CTA's half of the tile's columns)
 constexpr int kP2Smem = kP2Stages * kP2StageBytes + 1024;
-constexpr int kP2CPW = 2;                                             // 32-column chunks per epilogue warp (256 columns / 4 column parts)
 constexpr int kP2Levels = 4;
 constexpr int kP2FlushKB = 32;                                        // LSTM tiles with K >= 2048 restart the main chain at half K (shorter ones: their epilogue would serialise with the second half)                                          // linear1, LSTM-0, LSTM-1, linear2
 
@@ -811,7 +815,7 @@ rc_tc_phase_pair256_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl
     __shared__ __align__(8) uint64_t tq_full[kPhQ];
     __shared__ __align__(8) uint64_t tq_empty[kPhQ];
     __shared__ __align__(16) int4 tq_tile[kPhQ];
-    __shared__ int s_mb[RC_PH_MAXJOBS], s_nt[RC_PH_MAXJOBS], s_tw[RC_PH_MAXJOBS];   // per job: row-block pairs, column tiles per row block, tile width
+    __shared__ int s_mb[RC_PH_MAXJOBS], s_nt[RC_PH_MAXJOBS];   // per job: row-block pairs, column tiles per row block
     __shared__ int lvl_tile0[kP2Levels + 1], lvl_job0[kP2Levels + 1];
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) uint4 epi_buf[kPhEpiWarps][128];         // 2 KB per epilogue warp
@@ -834,7 +838,6 @@ rc_tc_phase_pair256_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl
     __syncthreads();
     if (threadIdx.x == 0) {
         // tile plan (identical in every CTA): jobs are stored level by level
-        const int npairs = (int)(gridDim.x >> 1);
         int lv = 0, total = 0;
         lvl_job0[0] = 0;
         for (int j = 0; j <= njobs; ++j) {
@@ -842,7 +845,7 @@ rc_tc_phase_pair256_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl
             while (lv < l) {                                        // close level lv: jobs lvl_job0[lv] .. j - 1
                 lvl_tile0[lv] = total;
                 for (int q = lvl_job0[lv]; q < j; ++q) {
-                    s_tw[q] = TW;                                  // the narrow jobs (linear2) too: a 144-column job takes two 128-column tiles
+                    // every job in tiles of TW columns — the narrow ones (linear2) too: a 144-column job takes two 128-column tiles
                     s_nt[q] = s_nm[q] == 256 ? s_n2[q] * (256 / TW) : (s_nm[q] + TW - 1) / TW;
                     total += s_mb[q] * s_nt[q];
                 }
@@ -1359,7 +1362,7 @@ int sm_count() {
 
 }  // namespace
 
-int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void* stream, long long* d_trace, int tile_width_hint) {
+int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void* stream, long long* d_trace, int tile_width_hint, int reserve_sms) {
     static int pair = -1;
     // Default: the single-CTA kernel (128-row tiles).  RC_PH_PAIR=1 selects the CTA-pair kernel (cta_group::2, 256-row tiles): 25 % less
     // L2 -> SM traffic, same main-loop rate (both sit at the shared-memory port), but the row lists of a frame (~768 / ~256 streams) end
@@ -1379,7 +1382,7 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
             RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_pair256_kernel<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kP2Smem));
             attr_set = true;
         }
-        const int pairs = std::max(1, std::min(sm_count() / 2, max_tiles));
+        const int pairs = std::max(1, std::min((sm_count() - reserve_sms) / 2, max_tiles));
         static int mix = -1;
         if (mix < 0) { const char* e = getenv("RC_PH_MIX"); mix = e ? atoi(e) : 0; }   // tile order inside a layer level (A/B switch)
         if (tw == 128) {
@@ -1398,7 +1401,7 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
             RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
             attr_set = true;
         }
-        const int pairs = std::max(1, std::min(sm_count() / 2, max_tiles));             // max_tiles bounds the 256-row tiles too
+        const int pairs = std::max(1, std::min((sm_count() - reserve_sms) / 2, max_tiles));   // max_tiles bounds the 256-row tiles too
         static int korder = -1;
         if (korder < 0) { const char* e = getenv("RC_PH_KORDER"); korder = e ? atoi(e) : 1; }   // 0: dependency wait before the first K block (A/B switch)
         RC_LAUNCH_PDL(rc_tc_phase_pair_kernel, 2 * pairs, kPhThreads, kPairSmem, stream, d_desc, d_ctl, MT, d_trace, korder);
@@ -1410,7 +1413,7 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
         RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
         attr_set = true;
     }
-    const int grid = std::max(1, std::min(sm_count(), max_tiles));
+    const int grid = std::max(1, std::min(sm_count() - reserve_sms, max_tiles));
     RC_LAUNCH(rc_tc_phase_kernel, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
     RC_CHECK_LAUNCH();
     return RC_OK;

@@ -38,7 +38,9 @@ struct alignas(64) RcPhDesc {
 // d_trace (debug, normally null): per tile 16 x int64 {cta<<32|job<<16|m<<8|n, t_grab, t_dep, t_mma0, t_commit, t_epi0, t_stored, t_done,
 // t_handed_back, then per 32-column chunk (LSTM jobs): t_tmem_read, t_math, t_stores_issued, ...} (clock64 of the SM)
 // tile_width_hint (256 x 256 CTA-pair kernel only): 256 or 128 columns per tile for the wide jobs
-int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void* stream, long long* d_trace = nullptr, int tile_width_hint = 256);
+// reserve_sms: SMs the persistent grid leaves free (for kernels of a concurrent stream: the resident CTAs take a whole SM each)
+int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void* stream, long long* d_trace = nullptr, int tile_width_hint = 256,
+                int reserve_sms = 0);
 
 // Gather + split pre-pass for all chains of a phase in one launch: segment i copies rows rows_i[0..*count_i) of src
 // ([*, ld], first K columns valid, zero up to Kout) into (hi, lo)[compact row * pitch + col0 ...]; also zeroes `zero[0..nzero)`.

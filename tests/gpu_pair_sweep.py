@@ -34,3 +34,6 @@ for i, c in enumerate(configs):
         print('    vs first config: pose max %.2e rad, 99.9 %% %.2e, tran max %.2e m, finite %s' % (
             an.max().item(), an.flatten().kthvalue(int(an.numel() * 0.999)).values.item(), (res['tran'] - ref['tran']).abs().max().item(),
             bool(torch.isfinite(res['pose']).all())), flush=True)
+        per_stream = an.amax(dim=(1, 2))
+        top = per_stream.topk(min(5, len(per_stream)))
+        print('    worst streams: ' + ', '.join('%d: %.2e' % (i, v) for v, i in zip(top.values.tolist(), top.indices.tolist())), flush=True)
