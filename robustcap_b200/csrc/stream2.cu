@@ -57,6 +57,7 @@ struct S2Args {
     int* gflags;                                    // [0] need_init (written by CTA 0)
     unsigned* bar;                                  // [2][16] grid-barrier words, one set per frame parity
     int parity;
+    int program;                                    // order of the frame's groups (s2_build)
     unsigned long long* ts;
 };
 struct S2Group { int kind, mask, wait_before, arrive_after, pre, late; };
@@ -110,23 +111,37 @@ __device__ __forceinline__ const S2Mat& s2_mat(const S2Net& n, int kind) {
 __device__ __forceinline__ int s2_units_per_chunk(int K) { return max(1, kS2SlotBytes / (K * 16)); }
 
 // The frame's program: the same list drives the producer (which slices to stream, in which order) and the consumers.
-__device__ int s2_build(int f, S2Group* g) {
+__device__ int s2_build(int f, S2Group* g, int program) {
     const bool hi = (f & RC_F_HI) != 0, r6b = (f & RC_F_R6B) != 0, late = (f & RC_F_LATE) != 0;
     const int p1 = (hi ? (1 << NET4) : 0) | (1 << NET2);
     const int p2 = (r6b ? (1 << NET6) : 0) | (1 << NET3) | (1 << NET7) | (1 << NET8);
     const int pl = (1 << NET4) | (1 << NET6);
     int n = 0;
     auto add = [&](int kind, int mask, int wait, int arrive, int pre, int lt) { g[n].kind = kind; g[n].mask = mask; g[n].wait_before = wait; g[n].arrive_after = arrive; g[n].pre = pre; g[n].late = lt; ++n; };
+    // The recurrent halves (LH*, no dependency inside the frame) sit between an arrive and the matching wait of the grid barriers, so the
+    // dependency latency is covered by streaming.  program 1 (default) spreads the second phase's halves — rnn6 apart from the three
+    // H = 512 nets — over four barrier gaps instead of two; program 0 is the former order (A/B: RC_S2_PROGRAM).
+    const int p2a = r6b ? (1 << NET6) : 0, p2b = (1 << NET3) | (1 << NET7) | (1 << NET8);
     add(PK_LIN1, p1, 0, 1, PRE_NONE, 0);
     add(PK_LH0, p1, 0, 0, PRE_NONE, 0);
     add(PK_LX0, p1, 1, 1, PRE_NONE, 0);
     add(PK_LH1, p1, 0, 0, PRE_NONE, 0);
     add(PK_LX1, p1, 1, 1, PRE_NONE, 0);
-    add(PK_LH0, p2, 0, 0, PRE_NONE, 0);
-    add(PK_LIN2, p1, 1, 1, PRE_NONE, 0);
-    add(PK_LH1, p2, 0, 0, PRE_NONE, 0);
-    add(PK_LIN1, p2, 1, 1, PRE_BLEND, 0);
-    add(PK_LX0, p2, 1, 1, PRE_NONE, 0);
+    if (program == 0 || !p2a) {
+        add(PK_LH0, p2, 0, 0, PRE_NONE, 0);
+        add(PK_LIN2, p1, 1, 1, PRE_NONE, 0);
+        add(PK_LH1, p2, 0, 0, PRE_NONE, 0);
+        add(PK_LIN1, p2, 1, 1, PRE_BLEND, 0);
+        add(PK_LX0, p2, 1, 1, PRE_NONE, 0);
+    } else {
+        add(PK_LH0, p2a, 0, 0, PRE_NONE, 0);
+        add(PK_LIN2, p1, 1, 1, PRE_NONE, 0);
+        add(PK_LH0, p2b, 0, 0, PRE_NONE, 0);
+        add(PK_LIN1, p2, 1, 1, PRE_BLEND, 0);
+        add(PK_LH1, p2a, 0, 0, PRE_NONE, 0);
+        add(PK_LX0, p2, 1, 1, PRE_NONE, 0);
+        add(PK_LH1, p2b, 0, 0, PRE_NONE, 0);
+    }
     add(PK_LX1, p2, 1, 1, PRE_NONE, 0);
     add(PK_LIN2, p2, 1, 1, PRE_NONE, 0);
     if (late) { add(PK_LH0, pl, 0, 0, PRE_NONE, 1); add(PK_LH1, pl, 0, 0, PRE_NONE, 1); }
@@ -166,7 +181,7 @@ __global__ void __launch_bounds__(kS2Threads, 1) rc_stream2_kernel(const __grid_
         inflags |= RC_F_ACTIVE;
         const int f = rc_prep_warp(a.cfg, a.row->vision_count, S.prep, io.j2dc + (long long)a.t * 99, io.accc + (long long)a.t * 18,
                                    io.oric + (long long)a.t * 54, inflags, S.x2, S.x3, S.x4, S.x6, S.x7, S.rcr, &S.conf, S.lerpw, lane);
-        if (lane == 0) { S.flags = f; S.ngroups = s2_build(f, S.groups); }
+        if (lane == 0) { S.flags = f; S.ngroups = s2_build(f, S.groups, a.program); }
     }
     __syncthreads();
     const int f = S.flags;
@@ -312,7 +327,9 @@ __global__ void __launch_bounds__(kS2Threads, 1) rc_stream2_kernel(const __grid_
         }
         // ---- the input vectors of all matrices of the group into shared memory, one barrier for the group.  Double-buffered by
         // group: a warp that loads group g has passed the barrier of group g - 1, which every warp only reaches after its reads of
-        // group g - 2 (the previous user of this buffer set).
+        // group g - 2 (the previous user of this buffer set).  (Tried: fetching the vectors of the next recurrent-half group into
+        // registers before the current group's weights are consumed — the recurrent groups got ~0.9 us shorter, the groups carrying
+        // the loads ~2.5 us longer; dropped.)
         {
             int k = 0;
             for (int ni = 0; ni < NNETS; ++ni) {
@@ -496,6 +513,8 @@ int rc_stream2_frame(rc_state* s, const StepIO& io, int t, void* stream) {
     for (int l = 0; l < 3; ++l) { a.Wi[l] = n->Wi[l]; a.bi[l] = n->bi[l]; }
     a.X4 = s->X4; a.X6 = s->X6; a.X7 = s->X7; a.Y3 = s->Y3; a.Y6 = s->Y6; a.Y7 = s->Y7; a.Y8 = s->Y8; a.I1 = s->I1; a.I2 = s->I2;
     a.gravity = s->gravity; a.gflags = (int*)(s->s2_bar + 48); a.bar = s->s2_bar; a.parity = s->s2_parity;
+    static const int program = getenv("RC_S2_PROGRAM") ? atoi(getenv("RC_S2_PROGRAM")) : 1;
+    a.program = program;
     static const bool want_ts = getenv("RC_STREAM_TS") != nullptr;
     if (want_ts && !s->s2_ts) { RC_CUDA(cudaMalloc(&s->s2_ts, (4 + 3 * kS2MaxGroups) * 8)); RC_CUDA(cudaMemsetAsync(s->s2_ts, 0, (4 + 3 * kS2MaxGroups) * 8, st)); }
     a.ts = want_ts ? s->s2_ts : nullptr;
