@@ -64,9 +64,15 @@ def test_synthesize_imu_vs_reference(rb, golden_dir, assets):
         assert (vimu.cpu() - g['imu_%s_vimu' % tag]).abs().max().item() < 2e-6, tag
         assert (joint.cpu() - g['imu_%s_joint' % tag]).abs().max().item() < 2e-6, tag
         assert (ori.cpu() - g['imu_%s_ori' % tag]).abs().max().item() < 2e-6, tag
-        # second differences x 3600 (x 900 smoothed) amplify 1e-6 m of float32 FK noise: bound the accelerations at 3e-2 m/s^2 and
-        # check the difference operator itself exactly on the kernel's own vertices
-        assert (acc.cpu() - g['imu_%s_acc' % tag]).abs().max().item() < 3e-2, tag
+        # The accelerations are second differences of the IMU vertices times 60^2 (_syn_acc): a vertex deviation e_v from the reference
+        # propagates as at most 4 * 3600 * e_v, plus the float32 rounding of the differences themselves (4 * 3600 * ulp(|v|)).  The bound is
+        # derived from the MEASURED vertex deviation of this run, not a constant; the difference operator itself is checked exactly on the
+        # kernel's own vertices below.
+        e_v = (vimu.cpu() - g['imu_%s_vimu' % tag]).abs().max().item()
+        bound = 4 * 3600 * (e_v + 1.2e-7 * g['imu_%s_vimu' % tag].abs().max().item())
+        e_a = (acc.cpu() - g['imu_%s_acc' % tag]).abs().max().item()
+        print('IMU synthesis (%s): vertex deviation %.2e m -> acceleration bound %.2e m/s^2, measured %.2e' % (tag, e_v, bound, e_a))
+        assert e_a <= bound, (tag, e_a, bound)
         from oracle.pipeline import syn_acc
         assert torch.equal(acc.cpu(), syn_acc(vimu.cpu())), tag
         acc4, _ = pipeline.synthesize_imu(body, g['imu_pose'], g['imu_tran'], shape, smooth_n=4)
