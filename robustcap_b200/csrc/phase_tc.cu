@@ -66,6 +66,17 @@ __device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kPhEpiWarps * 32) : "memory"); }
 
+// N256 = true (RC_PH_PAIR=3, opt-in experiment): the products A-hi x W-hi and A-hi x W-lo of a K step as ONE N = 256 MMA — the W-hi and
+// W-lo tiles are adjacent in the stage, the accumulators [main | corr] adjacent in tensor memory — followed by A-lo x W-hi (N = 128) into
+// corr: two MMA instructions per K step instead of three, A-hi read from shared memory once (36 instead of 40 KB of shared-memory traffic
+// per K step).  A tile's accumulators are then 256 columns; the two 256-column slots are a ring of SEGMENTS (see the MMA warp).
+// Measured (B = 1024, same box, alternating runs): with two segments per LSTM tile (h_prev half, x half) 540 / 528 us per frame against
+// 555 / 570 us (K = 2560 tiles 44 k -> 39-44 k clk of MMA issue), but one stream of test_grouped_kernel_odd_row_blocks[130] lands 1.21e-4 rad
+// from the float64 oracle (bound 1.2e-4; the three-buffer scheme with its two interleaved chains: <= 5.4e-5); with segments of <= 10 K
+// blocks (below) that stream is at 1.11e-4 and the gain is gone (544 / 555 vs 545 us: twice the drains).  Not the default.
+__device__ __forceinline__ int n256_segments(int KB) { return KB >= 32 ? 4 : (KB >= 16 ? 2 : 1); }
+
+template <bool N256>
 __global__ void __launch_bounds__(kPhThreads, 1)
 rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT, long long* __restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
@@ -74,6 +85,7 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
     __shared__ __align__(8) uint64_t bar_empty[kPhStages];
     __shared__ __align__(8) uint64_t bar_acc_full;
     __shared__ __align__(8) uint64_t bar_acc_free;
+    __shared__ __align__(8) uint64_t bar2_full[2], bar2_free[2];      // N256: per accumulator slot
     __shared__ __align__(8) uint64_t tq_full[kPhQ];
     __shared__ __align__(8) uint64_t tq_empty[kPhQ];
     __shared__ int4 tq_tile[kPhQ];
@@ -96,6 +108,7 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
         for (int s = 0; s < kPhStages; ++s) { mbar_init(smem_u32(&bar_full[s]), 1); mbar_init(smem_u32(&bar_empty[s]), 1); }
         mbar_init(smem_u32(&bar_acc_full), 1);
         mbar_init(smem_u32(&bar_acc_free), kPhEpiWarps);       // one arrival per epilogue warp
+        for (int q = 0; q < 2; ++q) { mbar_init(smem_u32(&bar2_full[q]), 1); mbar_init(smem_u32(&bar2_free[q]), kPhEpiWarps); }
         for (int q = 0; q < kPhQ; ++q) { mbar_init(smem_u32(&tq_full[q]), 1); mbar_init(smem_u32(&tq_empty[q]), 1 + kPhEpiWarps); }   // MMA thread + epilogue warps
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -171,7 +184,7 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
             // instruction descriptor (cute UMMA::InstrDescriptor): c_format F32 = 1 at [4,6); a/b format F16 = 0; K-major both;
             // n_dim = N >> 3 at [17,23); m_dim = M >> 4 at [24,29)
             const uint32_t idesc = (1u << 4) | ((uint32_t)(kPhBN >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
-            uint32_t it = 0;
+            uint32_t it = 0, gseg = 0;
             for (int q = 0;; ++q) {
                 const int slot = q % kPhQ;
                 mbar_wait(smem_u32(&tq_full[slot]), ((uint32_t)q / kPhQ) & 1u);
@@ -179,6 +192,41 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
                 mbar_arrive(smem_u32(&tq_empty[slot]));
                 if (t.x < 0) break;
                 const int KB = D->job[t.x].K / kTcBK;
+                if (N256) {
+                    // accumulator slots of 256 columns ([main | corr]) used as a ring of SEGMENTS of <= 10 K blocks in alternating slots: the
+                    // epilogue drains a segment into its registers while the next one accumulates, so the truncating accumulate chains are at
+                    // most 40 steps long (three-buffer scheme: two interleaved chains of up to 80) and the MMA stream has no bubble.
+                    const int nseg = n256_segments(KB), KBs = KB / nseg;
+                    const uint32_t idesc2 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+                    if (trace) trace[(size_t)t.w * 16 + 3] = clock64();
+                    for (int sg = 0; sg < nseg; ++sg, ++gseg) {
+                        const int sl = (int)(gseg & 1u);
+                        if (gseg > 1) {                         // the segment before the previous one has left this slot
+                            mbar_wait(smem_u32(&bar2_free[sl]), ((gseg >> 1) - 1u) & 1u);
+                            tc_fence_after();
+                        }
+                        const uint32_t d_main = tmem_base + (uint32_t)(sl * 256), d_cr = d_main + 128u;
+                        for (int kb = 0; kb < KBs; ++kb, ++it) {
+                            const int s = it % kPhStages;
+                            const uint32_t ph = (it / kPhStages) & 1u;
+                            mbar_wait(smem_u32(&bar_full[s]), ph);
+                            tc_fence_after();
+                            const uint32_t base = smem_u32(smem + (size_t)s * kPhStageBytes);
+                            const uint64_t dAhi = make_desc(base), dAlo = make_desc(base + kPhABytes);
+                            const uint64_t dWhi = make_desc(base + 2 * kPhABytes);       // [W-hi | W-lo]: 256 rows of 128 bytes
+#pragma unroll
+                            for (int k = 0; k < kTcBK / 16; ++k) {
+                                const uint64_t adv = (uint64_t)(k * 2);
+                                tc_mma_f16(d_main, dAhi + adv, dWhi + adv, idesc2, (kb | k) ? 1u : 0u);
+                                tc_mma_f16(d_cr, dAlo + adv, dWhi + adv, idesc, 1u);
+                            }
+                            tc_commit(smem_u32(&bar_empty[s]));
+                        }
+                        tc_commit(smem_u32(&bar2_full[sl]));
+                    }
+                    if (trace) trace[(size_t)t.w * 16 + 4] = clock64();
+                    continue;
+                }
                 if (q > 0) {                                    // the previous tile's corr / main-0 are in registers
                     mbar_wait(smem_u32(&bar_acc_free), (uint32_t)(q - 1) & 1u);
                     tc_fence_after();
@@ -213,6 +261,7 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
         const int ewarp = warp - 2;
         const int q4 = warp & 3, part = ewarp >> 2;             // a warp may only read TMEM lanes 32 * (warp_id % 4) ..; part = its share of the columns
         const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+        uint32_t eseg = 0;                                       // N256: accumulator segments consumed so far
         for (int q = 0;; ++q) {
             const int slot = q % kPhQ;
             mbar_wait(smem_u32(&tq_full[slot]), ((uint32_t)q / kPhQ) & 1u);
@@ -239,11 +288,36 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
             const uint32_t b_corr = (uint32_t)(((3 * q) & 3) * kPhBN);
             const uint32_t b_m0 = (uint32_t)(((3 * q + 1) & 3) * kPhBN);
             const uint32_t b_m1 = (uint32_t)(((3 * q + 2) & 3) * kPhBN);
+            float acc[kPhCPW * 32];
+            if (N256) {
+                const int nseg = n256_segments(J.K / kTcBK);
+                for (int sg = 0; sg < nseg; ++sg, ++eseg) {
+                    const uint32_t sl = eseg & 1u;
+                    mbar_wait(smem_u32(&bar2_full[sl]), (eseg >> 1) & 1u);
+                    tc_fence_after();
+                    if (sg == nseg - 1 && trace && ewarp == 0 && lane == 0) trace[(size_t)t.w * 16 + 5] = clock64();
+#pragma unroll
+                    for (int cc = 0; cc < 2 * kPhCPW; ++cc) {                   // 16 columns at a time: 32 accumulators + 32 in flight
+                        const uint32_t col = sl * 256u + (uint32_t)(part * kPhCPW * 32 + cc * 16);
+                        uint32_t v0[16], v1[16];
+                        tc_ld16(lane_base + col, v0);
+                        tc_ld16(lane_base + col + 128u, v1);
+                        tc_ld_wait();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            const float x = fmaf(__uint_as_float(v1[e]), 4.8828125e-4f, __uint_as_float(v0[e]));   // main + corr * 2^-11 of this half
+                            acc[cc * 16 + e] = sg ? acc[cc * 16 + e] + x : x;
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar2_free[sl]));
+                }
+            } else {
             mbar_wait(smem_u32(&bar_acc_full), (uint32_t)q & 1u);
             tc_fence_after();
             if (trace && ewarp == 0 && lane == 0) trace[(size_t)t.w * 16 + 5] = clock64();
             // phase A: corr and main-0 of this thread's columns into registers, then the two buffers go back to the MMA warp
-            float acc[kPhCPW * 32];
 #pragma unroll
             for (int cc = 0; cc < kPhCPW; ++cc) {
                 const uint32_t col = (uint32_t)((part * kPhCPW + cc) * 32);
@@ -257,17 +331,20 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bar_acc_free));
+            }
             if (trace && ewarp == 0 && lane == 0) trace[(size_t)t.w * 16 + 8] = clock64();
             // phase B: main-1, gate math, stores
 #pragma unroll
             for (int cc = 0; cc < kPhCPW; ++cc) {
                 const int c = part * kPhCPW + cc;
-                uint32_t v0[32];
-                tc_ld32(lane_base + b_m1 + (uint32_t)(c * 32), v0);
-                tc_ld_wait();
                 float* a = acc + cc * 32;
+                if (!N256) {
+                    uint32_t v0[32];
+                    tc_ld32(lane_base + b_m1 + (uint32_t)(c * 32), v0);
+                    tc_ld_wait();
 #pragma unroll
-                for (int e = 0; e < 32; ++e) a[e] += __uint_as_float(v0[e]);
+                    for (int e = 0; e < 32; ++e) a[e] += __uint_as_float(v0[e]);
+                }
                 if (trace && ewarp == 0 && lane == 0) trace[(size_t)t.w * 16 + 9 + cc * 3] = clock64();
                 if (row < 0) continue;
                 const int nb = n0 + c * 32;
@@ -1395,7 +1472,7 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
         RC_CHECK_LAUNCH();
         return RC_OK;
     }
-    if (pair) {
+    if (pair == 1) {
         static bool attr_set = false;
         if (!attr_set) {
             RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem));
@@ -1410,11 +1487,13 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
     }
     static bool attr_set = false;
     if (!attr_set) {
-        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
+        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
+        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
         attr_set = true;
     }
     const int grid = std::max(1, std::min(sm_count() - reserve_sms, max_tiles));
-    RC_LAUNCH(rc_tc_phase_kernel, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
+    if (pair == 3) RC_LAUNCH(rc_tc_phase_kernel<true>, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
+    else RC_LAUNCH(rc_tc_phase_kernel<false>, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
     RC_CHECK_LAUNCH();
     return RC_OK;
 }
