@@ -73,10 +73,12 @@ __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" 
 // Measured (B = 1024, same box, alternating runs): with two segments per LSTM tile (h_prev half, x half) 540 / 528 us per frame against
 // 555 / 570 us (K = 2560 tiles 44 k -> 39-44 k clk of MMA issue), but one stream of test_grouped_kernel_odd_row_blocks[130] lands 1.21e-4 rad
 // from the float64 oracle (bound 1.2e-4; the three-buffer scheme with its two interleaved chains: <= 5.4e-5); with segments of <= 10 K
-// blocks (below) that stream is at 1.11e-4 and the gain is gone (544 / 555 vs 545 us: twice the drains).  Not the default.
+// blocks (below) that stream is at 1.11e-4 and the gain is gone (544 / 555 vs 545 us: twice the drains).  N256 = 2 (RC_PH_PAIR=4) keeps the
+// default's K-step-interleaved chains (even steps -> slot 0, odd -> slot 1, both slots per tile): default-grade accuracy, +1 %.  Neither is
+// the default (profiles/r03_pair256.md).
 __device__ __forceinline__ int n256_segments(int KB) { return KB >= 32 ? 4 : (KB >= 16 ? 2 : 1); }
 
-template <bool N256>
+template <int N256>                                    // 0: three accumulators (default), 1: fused MMA + segment ring, 2: fused MMA + interleaved chains
 __global__ void __launch_bounds__(kPhThreads, 1)
 rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT, long long* __restrict__ trace) {
     extern __shared__ uint8_t smem_raw[];
@@ -192,6 +194,38 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
                 mbar_arrive(smem_u32(&tq_empty[slot]));
                 if (t.x < 0) break;
                 const int KB = D->job[t.x].K / kTcBK;
+                if (N256 == 2) {
+                    // fused MMA with the accumulate chains of the default scheme: even K steps into slot 0 ([main-0 | corr-0]), odd ones into
+                    // slot 1 ([main-1 | corr-1]) — main is the same two K-step-interleaved chains, corr two instead of one.  Both slots
+                    // belong to one tile; the next tile's first even step waits for slot 0 only, its first odd step for slot 1.
+                    const uint32_t idesc2 = (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+                    if (trace) trace[(size_t)t.w * 16 + 3] = clock64();
+                    int g = 0;
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        const int s = it % kPhStages;
+                        const uint32_t ph = (it / kPhStages) & 1u;
+                        mbar_wait(smem_u32(&bar_full[s]), ph);
+                        tc_fence_after();
+                        const uint32_t base = smem_u32(smem + (size_t)s * kPhStageBytes);
+                        const uint64_t dAhi = make_desc(base), dAlo = make_desc(base + kPhABytes);
+                        const uint64_t dWhi = make_desc(base + 2 * kPhABytes);       // [W-hi | W-lo]: 256 rows of 128 bytes
+#pragma unroll
+                        for (int k = 0; k < kTcBK / 16; ++k, ++g) {
+                            if (g < 2 && q > 0) {                   // the previous tile has left this slot
+                                mbar_wait(smem_u32(&bar2_free[g]), (uint32_t)(q - 1) & 1u);
+                                tc_fence_after();
+                            }
+                            const uint64_t adv = (uint64_t)(k * 2);
+                            const uint32_t d_main = tmem_base + (uint32_t)((g & 1) * 256);
+                            tc_mma_f16(d_main, dAhi + adv, dWhi + adv, idesc2, g >= 2 ? 1u : 0u);
+                            tc_mma_f16(d_main + 128u, dAlo + adv, dWhi + adv, idesc, 1u);
+                        }
+                        tc_commit(smem_u32(&bar_empty[s]));
+                    }
+                    tc_commit(smem_u32(&bar_acc_full));
+                    if (trace) trace[(size_t)t.w * 16 + 4] = clock64();
+                    continue;
+                }
                 if (N256) {
                     // accumulator slots of 256 columns ([main | corr]) used as a ring of SEGMENTS of <= 10 K blocks in alternating slots: the
                     // epilogue drains a segment into its registers while the next one accumulates, so the truncating accumulate chains are at
@@ -289,7 +323,33 @@ rc_tc_phase_kernel(const RcPhDesc* __restrict__ D, int* __restrict__ ctl, int MT
             const uint32_t b_m0 = (uint32_t)(((3 * q + 1) & 3) * kPhBN);
             const uint32_t b_m1 = (uint32_t)(((3 * q + 2) & 3) * kPhBN);
             float acc[kPhCPW * 32];
-            if (N256) {
+            if (N256 == 2) {
+                mbar_wait(smem_u32(&bar_acc_full), (uint32_t)q & 1u);
+                tc_fence_after();
+                if (trace && ewarp == 0 && lane == 0) trace[(size_t)t.w * 16 + 5] = clock64();
+                const bool one = J.K / 16 < 2;                      // a single K step never touches slot 1
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (!(sl && one)) {
+#pragma unroll
+                        for (int cc = 0; cc < 2 * kPhCPW; ++cc) {
+                            const uint32_t col = (uint32_t)(sl * 256 + part * kPhCPW * 32 + cc * 16);
+                            uint32_t v0[16], v1[16];
+                            tc_ld16(lane_base + col, v0);
+                            tc_ld16(lane_base + col + 128u, v1);
+                            tc_ld_wait();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) {
+                                const float x = fmaf(__uint_as_float(v1[e]), 4.8828125e-4f, __uint_as_float(v0[e]));   // main-s + corr-s * 2^-11
+                                acc[cc * 16 + e] = sl ? acc[cc * 16 + e] + x : x;
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bar2_free[sl]));
+                }
+            } else if (N256) {
                 const int nseg = n256_segments(J.K / kTcBK);
                 for (int sg = 0; sg < nseg; ++sg, ++eseg) {
                     const uint32_t sl = eseg & 1u;
@@ -1487,13 +1547,15 @@ int rc_tc_phase(const RcPhDesc* d_desc, int* d_ctl, int MT, int max_tiles, void*
     }
     static bool attr_set = false;
     if (!attr_set) {
-        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
-        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
+        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
+        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
+        RC_CUDA(cudaFuncSetAttribute(rc_tc_phase_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPhSmem));
         attr_set = true;
     }
     const int grid = std::max(1, std::min(sm_count() - reserve_sms, max_tiles));
-    if (pair == 3) RC_LAUNCH(rc_tc_phase_kernel<true>, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
-    else RC_LAUNCH(rc_tc_phase_kernel<false>, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
+    if (pair == 3) RC_LAUNCH(rc_tc_phase_kernel<1>, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
+    else if (pair == 4) RC_LAUNCH(rc_tc_phase_kernel<2>, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
+    else RC_LAUNCH(rc_tc_phase_kernel<0>, grid, kPhThreads, kPhSmem, stream, d_desc, d_ctl, MT, d_trace);
     RC_CHECK_LAUNCH();
     return RC_OK;
 }
