@@ -1006,6 +1006,8 @@ int rc_forward_online(rc_state* s, const float* j2dc, const float* accc, const f
         memcpy(s->on_hin + 117, oric, 54 * sizeof(float));
         if (first_tran) memcpy(s->on_hin + 171, first_tran, 3 * sizeof(float));
         memcpy(s->on_hin + 174, &flags, sizeof(int));
+        // (Tried: no copy — the single-launch kernel reading the frame straight out of the pinned host buffer, as it writes pose / tran into
+        // it: 148 CTAs fetching the 700 bytes over PCIe at kernel start cost +27 us of p50, 168-172 vs 141-143 us.)
         RC_CUDA(cudaMemcpyAsync(s->on_din, s->on_hin, kOnIn * sizeof(float), cudaMemcpyHostToDevice, st));
     }
     StepIO io;
