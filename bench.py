@@ -113,10 +113,12 @@ class ClockSampler:
 
 def dominant_traffic(gemm_mode=1):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full capture
-    (profiles/r01_tc_traffic.json, written from the .ncu-rep by profiles/extract_traffic.py); None when absent."""
-    path = os.path.join(REPO, 'profiles', 'r01_phase_traffic.json' if gemm_mode == 2 else 'r01_tc_traffic.json')
-    if os.path.exists(path):
-        return json.load(open(path)).get('dram_bytes_per_launch')
+    (profiles/r03_phase_traffic.json for the grouped kernel, written from the .ncu-rep by profiles/extract_phase.py); None when absent."""
+    names = ('r03_phase_traffic.json', 'r01_phase_traffic.json') if gemm_mode == 2 else ('r01_tc_traffic.json',)   # newest capture first
+    for name in names:
+        path = os.path.join(REPO, 'profiles', name)
+        if os.path.exists(path):
+            return json.load(open(path)).get('dram_bytes_per_launch')
     return None
 
 
